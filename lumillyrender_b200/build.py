@@ -1,0 +1,71 @@
+"""Builds liblumilly_b200.so (CUDA kernels + C ABI + host front end) in-tree for sm_100a.
+
+nvcc cross-compiles without a GPU; the built .so is git-ignored but travels to the GPU box with
+the gpurun snapshot.  Flags:
+  -gencode arch=compute_100a,code=sm_100a   B200 only, no PTX for other targets
+  -fmad=false                               no FMA contraction in device code (numerics contract,
+                                            csrc/device_path.cuh)
+  -Xcompiler -ffp-contract=off              same for the host fp32 set-up code
+  -lineinfo                                 so ncu's source page maps to our code
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "liblumilly_b200.so")
+CLI = os.path.join(HERE, "bin", "lumilly")
+SOURCES = ["kernels.cu", "api.cpp", "bvh_build.cpp", "toml_obj.cpp", "host_scene.cpp", "image_io.cpp"]
+HEADERS = ["device_scene.h", "device_path.cuh", "kernels.h", "common.h", "host_scene.h", "../../include/lumilly.h"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: liblumilly_b200 cannot be built (there is no CPU fallback)")
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build_library(force=False, verbose=False):
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    if not force and not _stale(LIB, deps):
+        return LIB
+    cmd = [
+        _nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
+        "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
+        "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-fvisibility=default",
+        "-shared", "-o", LIB,
+    ] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lz"]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+def build_cli(force=False):
+    src = os.path.join(CSRC, "cli_main.cpp")
+    if not os.path.exists(src):
+        return None
+    build_library(force=force)
+    if not force and not _stale(CLI, [src, LIB]):
+        return CLI
+    os.makedirs(os.path.dirname(CLI), exist_ok=True)
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", CLI, src, "-L" + HERE, "-llumilly_b200",
+           "-Wl,-rpath,$ORIGIN/..", "-I" + os.path.join(HERE, "..", "include")]
+    subprocess.run(cmd, check=True)
+    return CLI
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_cli(force="--force" in sys.argv))

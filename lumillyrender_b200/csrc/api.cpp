@@ -1,0 +1,437 @@
+// api.cpp — C ABI of liblumilly_b200.so: scene upload, render, probes, measurement helpers.
+// The boundary replaces main.rs:70-132 (see include/lumilly.h).  No CPU fallback exists: every
+// compute entry point needs a CUDA device and fails with LR_ERR_NO_DEVICE / LR_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "kernels.h"
+
+namespace lr {
+
+thread_local std::string g_error;
+void set_error(const std::string& s) { g_error = s; }
+int fail(int code, const std::string& s) { g_error = s; return code; }
+
+static int g_device = -1;
+static int g_sm_count = 0;
+
+#define LR_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return fail(LR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));       \
+  } while (0)
+
+static int ensure_device() {
+  if (g_device >= 0) return LR_OK;
+  return lr_init(0);
+}
+
+template <class T>
+static cudaError_t upload(const std::vector<T>& h, const T** d, uint64_t& bytes) {
+  *d = nullptr;
+  if (h.empty()) return cudaSuccess;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, h.size() * sizeof(T));
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(p); return e; }
+  *d = (const T*)p;
+  bytes += h.size() * sizeof(T);
+  return cudaSuccess;
+}
+
+static inline float4 mk4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+static inline float as_float(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
+
+}  // namespace lr
+
+using namespace lr;
+
+struct LrScene {
+  DevScene dev{};
+  std::vector<void*> allocs;
+  uint64_t h2d_bytes = 0;
+  int width = 0, height = 0;
+  unsigned long long* d_counters = nullptr;
+  // scratch (mutable: owned by the handle, one caller thread at a time per LrScene)
+  mutable float* d_partial = nullptr; mutable size_t partial_floats = 0;
+  mutable float* d_partial_sq = nullptr; mutable size_t partial_sq_floats = 0;
+  mutable uint64_t acc_samples = 0;
+  mutable int acc_launches = 0;
+  mutable int last_splits = 1;
+  mutable float acc_kernel_ms = 0.0f;
+  mutable cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  mutable bool ev_pending = false;
+};
+
+extern "C" {
+
+int lr_abi_version(void) { return LR_ABI_VERSION; }
+const char* lr_last_error(void) { return g_error.c_str(); }
+
+int lr_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(LR_ERR_NO_DEVICE, std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                                      "); liblumilly_b200 has no CPU fallback");
+  if (device < 0 || device >= n) return fail(LR_ERR_INVALID, "device index out of range");
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(LR_ERR_NO_DEVICE, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(LR_ERR_NO_DEVICE, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+  g_device = device;
+  g_sm_count = prop.multiProcessorCount;
+  return LR_OK;
+}
+
+void lr_shutdown(void) { g_device = -1; }
+
+int lr_device_info(int* sm_count, int* l2_bytes, int* sm_clock_khz, char* name, int name_len) {
+  if (int rc = ensure_device()) return rc;
+  cudaDeviceProp prop;
+  LR_CUDA(cudaGetDeviceProperties(&prop, g_device));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (l2_bytes) *l2_bytes = prop.l2CacheSize;
+  if (sm_clock_khz) { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g_device); *sm_clock_khz = khz; }
+  if (name && name_len > 0) { std::strncpy(name, prop.name, name_len - 1); name[name_len - 1] = 0; }
+  return LR_OK;
+}
+
+int lr_scene_create(const LrSceneDesc* d, LrScene** out) {
+  if (!d || !out) return fail(LR_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (int rc = validate_desc(*d)) return rc;
+  if (int rc = ensure_device()) return rc;
+
+  // ---- pack host-side arrays (layout documented in device_scene.h)
+  std::vector<float4> nodes((size_t)d->n_nodes * 4), tris((size_t)d->n_triangles * 3), spheres(d->n_spheres), mats((size_t)d->n_materials * 3);
+  std::vector<int2> sphere_meta(d->n_spheres);
+  std::memcpy(nodes.data(), d->nodes, (size_t)d->n_nodes * sizeof(LrBvhNode));
+  for (int i = 0; i < d->n_triangles; i++) {
+    const LrTriangle& t = d->triangles[i];
+    tris[3 * (size_t)i + 0] = mk4(t.p0[0], t.p0[1], t.p0[2], as_float(t.prim_id));
+    tris[3 * (size_t)i + 1] = mk4(t.p1[0], t.p1[1], t.p1[2], as_float(t.material));
+    tris[3 * (size_t)i + 2] = mk4(t.p2[0], t.p2[1], t.p2[2], 0.0f);
+  }
+  for (int i = 0; i < d->n_spheres; i++) {
+    const LrSphere& s = d->spheres[i];
+    spheres[i] = mk4(s.center[0], s.center[1], s.center[2], s.radius);
+    sphere_meta[i].x = s.material; sphere_meta[i].y = s.prim_id;
+  }
+  std::vector<char> emissive(d->n_materials, 0);
+  for (int i = 0; i < d->n_materials; i++) {
+    const LrMaterial& m = d->materials[i];
+    // only Lambert carries emission (description.rs:94-101; every other material returns zero, e.g. ggx.rs:60-62)
+    const bool lam = m.type == LR_MAT_LAMBERT;
+    const float ex = lam ? m.emission[0] : 0.0f, ey = lam ? m.emission[1] : 0.0f, ez = lam ? m.emission[2] : 0.0f;
+    const float sq = ex * ex + ey * ey + ez * ez;                       // emission().sqr_norm() > 0.0 (objects.rs:21)
+    emissive[i] = sq > 0.0f;
+    const float weight = std::fmax(std::fmax(m.color[0], m.color[1]), m.color[2]);   // lambert.rs:27-30
+    mats[3 * (size_t)i + 0] = mk4(m.color[0], m.color[1], m.color[2], as_float(m.type));
+    mats[3 * (size_t)i + 1] = mk4(ex, ey, ez, m.param0);
+    mats[3 * (size_t)i + 2] = mk4(m.param1, weight, emissive[i] ? 1.0f : 0.0f, 0.0f);
+  }
+  // ---- emitter table in instance (prim_id) order: objects.rs:18-29
+  struct Em { int prim; float4 a, b, c; float area; };
+  std::vector<Em> ems;
+  for (int i = 0; i < d->n_triangles; i++) {
+    const LrTriangle& t = d->triangles[i];
+    if (!emissive[t.material]) continue;
+    Em e; e.prim = t.prim_id; e.area = triangle_area(t.p0, t.p1, t.p2);
+    e.a = mk4(t.p0[0], t.p0[1], t.p0[2], as_float(0));
+    e.b = mk4(t.p1[0], t.p1[1], t.p1[2], e.area);
+    e.c = mk4(t.p2[0], t.p2[1], t.p2[2], 0.0f);
+    ems.push_back(e);
+  }
+  for (int i = 0; i < d->n_spheres; i++) {
+    const LrSphere& s = d->spheres[i];
+    if (!emissive[s.material]) continue;
+    Em e; e.prim = s.prim_id; e.area = sphere_area(s.radius);
+    e.a = mk4(s.center[0], s.center[1], s.center[2], as_float(1));
+    e.b = mk4(s.radius, 0.0f, 0.0f, e.area);
+    e.c = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    ems.push_back(e);
+  }
+  std::sort(ems.begin(), ems.end(), [](const Em& x, const Em& y) { return x.prim < y.prim; });
+  std::vector<float> cdf(ems.size());
+  std::vector<float4> emitters(ems.size() * 3);
+  float area = 0.0f;
+  for (size_t i = 0; i < ems.size(); i++) {
+    area += ems[i].area;                                                // `area += obj.area()` objects.rs:41
+    cdf[i] = area;
+    emitters[3 * i] = ems[i].a; emitters[3 * i + 1] = ems[i].b; emitters[3 * i + 2] = ems[i].c;
+  }
+  std::vector<float4> sky;
+  if (d->sky.type == LR_SKY_IBL) {
+    const size_t all = 2 * (size_t)d->sky.height * d->sky.height;
+    sky.resize(all);
+    for (size_t i = 0; i < all; i++) sky[i] = mk4(d->sky.pixels[3 * i], d->sky.pixels[3 * i + 1], d->sky.pixels[3 * i + 2], 0.0f);
+  }
+
+  // ---- upload
+  LrScene* s = new LrScene();
+  auto track = [&](const void* p) { if (p) s->allocs.push_back(const_cast<void*>(p)); };
+  cudaError_t e = cudaSuccess;
+  DevScene& dv = s->dev;
+  if (e == cudaSuccess) { e = upload(nodes, &dv.nodes, s->h2d_bytes); track(dv.nodes); }
+  if (e == cudaSuccess) { e = upload(tris, &dv.tris, s->h2d_bytes); track(dv.tris); }
+  if (e == cudaSuccess) { e = upload(spheres, &dv.spheres, s->h2d_bytes); track(dv.spheres); }
+  if (e == cudaSuccess) { e = upload(sphere_meta, &dv.sphere_meta, s->h2d_bytes); track(dv.sphere_meta); }
+  if (e == cudaSuccess) { e = upload(mats, &dv.mats, s->h2d_bytes); track(dv.mats); }
+  if (e == cudaSuccess) { e = upload(cdf, &dv.emitter_cdf, s->h2d_bytes); track(dv.emitter_cdf); }
+  if (e == cudaSuccess) { e = upload(emitters, &dv.emitters, s->h2d_bytes); track(dv.emitters); }
+  if (e == cudaSuccess) { e = upload(sky, &dv.sky_pixels, s->h2d_bytes); track(dv.sky_pixels); }
+  if (e == cudaSuccess) { e = cudaMalloc((void**)&s->d_counters, C_COUNT * sizeof(unsigned long long)); }
+  if (e == cudaSuccess) { e = cudaMemset(s->d_counters, 0, C_COUNT * sizeof(unsigned long long)); }
+  if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+  if (e != cudaSuccess) {
+    const std::string msg = std::string("scene upload: ") + cudaGetErrorString(e);
+    lr_scene_destroy(s);
+    return fail(LR_ERR_CUDA, msg);
+  }
+  dv.n_nodes = d->n_nodes; dv.n_tris = d->n_triangles; dv.n_spheres = d->n_spheres; dv.n_emitters = (int)ems.size();
+  dv.emission_area = area;
+  dv.sky_type = d->sky.type;
+  dv.sky_color[0] = d->sky.color[0]; dv.sky_color[1] = d->sky.color[1]; dv.sky_color[2] = d->sky.color[2];
+  dv.sky_height = d->sky.height;
+  dv.sky_longitude_offset = d->sky.longitude_offset;
+  dv.cam = d->camera;
+  s->width = d->camera.width; s->height = d->camera.height;
+  *out = s;
+  return LR_OK;
+}
+
+void lr_scene_destroy(LrScene* s) {
+  if (!s) return;
+  for (void* p : s->allocs) cudaFree(p);
+  if (s->d_counters) cudaFree(s->d_counters);
+  if (s->d_partial) cudaFree(s->d_partial);
+  if (s->d_partial_sq) cudaFree(s->d_partial_sq);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  delete s;
+}
+
+int lr_scene_bytes(const LrScene* s, uint64_t* h2d_bytes) {
+  if (!s || !h2d_bytes) return fail(LR_ERR_INVALID, "null argument");
+  *h2d_bytes = s->h2d_bytes;
+  return LR_OK;
+}
+
+static int resolve_params(const LrScene* s, const LrRenderParams* p, DevParams& dp) {
+  if (!s || !p) return fail(LR_ERR_INVALID, "null argument");
+  if (p->integrator != LR_INTEGRATOR_PT && p->integrator != LR_INTEGRATOR_PT_DIRECT)
+    return fail(LR_ERR_INVALID, "Unknown integrator type");            // main.rs:124
+  if (p->spp_count <= 0 || p->spp_begin < 0) return fail(LR_ERR_INVALID, "spp range must be non-empty and non-negative");
+  if (p->depth < 0 || p->depth_limit < 0) return fail(LR_ERR_INVALID, "depth and depth_limit must be >= 0");
+  dp.integrator = p->integrator;
+  dp.spp_begin = p->spp_begin; dp.spp_count = p->spp_count;
+  dp.depth = p->depth; dp.depth_limit = p->depth_limit; dp.no_direct_emitter = p->no_direct_emitter ? 1 : 0;
+  dp.seed = p->seed;
+  if (p->crop_w > 0) {
+    if (p->crop_h <= 0 || p->crop_x < 0 || p->crop_y < 0 || p->crop_x + p->crop_w > s->width || p->crop_y + p->crop_h > s->height)
+      return fail(LR_ERR_INVALID, "crop window outside the film");
+    dp.crop_x = p->crop_x; dp.crop_y = p->crop_y; dp.crop_w = p->crop_w; dp.crop_h = p->crop_h;
+  } else {
+    dp.crop_x = 0; dp.crop_y = 0; dp.crop_w = s->width; dp.crop_h = s->height;
+  }
+  dp.tiles_x = (dp.crop_w + 7) / 8; dp.tiles_y = (dp.crop_h + 3) / 4;
+  int splits = p->splits;
+  if (splits <= 0) {
+    // auto: enough threads for ~2 full waves of 148 SMs x 2048 resident threads, >= 4 samples per thread
+    const long long px_threads = (long long)dp.tiles_x * dp.tiles_y * 32;
+    const long long target = 2LL * std::max(g_sm_count, 1) * 2048;
+    splits = (int)std::min<long long>((target + px_threads - 1) / px_threads, std::max(1, p->spp_count / 4));
+  }
+  splits = std::max(1, std::min(splits, p->spp_count));
+  // partial buffers must stay modest (<= 1 GiB)
+  const size_t px = (size_t)dp.crop_w * dp.crop_h;
+  while (splits > 1 && px * 3 * sizeof(float) * splits > (1ull << 30)) splits--;
+  dp.splits = splits;
+  return LR_OK;
+}
+
+static int ensure_scratch(float** buf, size_t* have, size_t need) {
+  if (*have >= need) return LR_OK;
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr; *have = 0;
+  LR_CUDA(cudaMalloc((void**)buf, need * sizeof(float)));
+  *have = need;
+  return LR_OK;
+}
+
+int lr_render_accumulate_device(const LrScene* s, const LrRenderParams* p, float* d_sum, float* d_sumsq, void* cuda_stream) {
+  DevParams dp;
+  if (int rc = resolve_params(s, p, dp)) return rc;
+  if (!d_sum) return fail(LR_ERR_INVALID, "d_sum is null");
+  if (int rc = ensure_device()) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const size_t n = (size_t)dp.crop_w * dp.crop_h * 3;
+  float* ksum = d_sum; float* ksq = d_sumsq;
+  if (dp.splits > 1) {
+    if (int rc = ensure_scratch(&s->d_partial, &s->partial_floats, n * dp.splits)) return rc;
+    ksum = s->d_partial;
+    if (d_sumsq) {
+      if (int rc = ensure_scratch(&s->d_partial_sq, &s->partial_sq_floats, n * dp.splits)) return rc;
+      ksq = s->d_partial_sq;
+    }
+  }
+  if (s->ev_pending) {   // fold the previous launch's time before reusing the events
+    float ms = 0.0f;
+    if (cudaEventSynchronize(s->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) s->acc_kernel_ms += ms;
+    s->ev_pending = false;
+  }
+  LR_CUDA(cudaEventRecord(s->ev0, st));
+  LR_CUDA(launch_render(s->dev, dp, p->count_traversal != 0, d_sumsq != nullptr, ksum, ksq, s->d_counters, st));
+  s->acc_launches++;
+  if (dp.splits > 1) {
+    LR_CUDA(launch_reduce_splits(d_sum, s->d_partial, n, dp.splits, st));
+    s->acc_launches++;
+    if (d_sumsq) { LR_CUDA(launch_reduce_splits(d_sumsq, s->d_partial_sq, n, dp.splits, st)); s->acc_launches++; }
+  }
+  LR_CUDA(cudaEventRecord(s->ev1, st));
+  s->ev_pending = true;
+  s->acc_samples += (uint64_t)dp.crop_w * dp.crop_h * (uint64_t)dp.spp_count;
+  s->last_splits = dp.splits;
+  return LR_OK;
+}
+
+int lr_stats_fetch(const LrScene* s, void* cuda_stream, LrStats* stats) {
+  if (!s || !stats) return fail(LR_ERR_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  LR_CUDA(cudaStreamSynchronize(st));
+  if (s->ev_pending) {
+    float ms = 0.0f;
+    LR_CUDA(cudaEventSynchronize(s->ev1));
+    LR_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->acc_kernel_ms += ms;
+    s->ev_pending = false;
+  }
+  unsigned long long c[C_COUNT];
+  LR_CUDA(cudaMemcpy(c, s->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+  LR_CUDA(cudaMemset(s->d_counters, 0, sizeof(c)));
+  std::memset(stats, 0, sizeof(*stats));
+  stats->rays = c[C_RAYS]; stats->nonfinite_samples = c[C_NONFINITE];
+  stats->nodes_visited = c[C_NODES]; stats->tris_tested = c[C_TRIS]; stats->spheres_tested = c[C_SPHERES];
+  stats->samples = s->acc_samples; stats->kernel_ms = s->acc_kernel_ms; stats->launches = s->acc_launches; stats->splits = s->last_splits;
+  s->acc_samples = 0; s->acc_kernel_ms = 0.0f; s->acc_launches = 0;
+  return LR_OK;
+}
+
+int lr_render(const LrScene* s, const LrRenderParams* p, float* out_rgb, float* out_sumsq, LrStats* stats) {
+  DevParams dp;
+  if (int rc = resolve_params(s, p, dp)) return rc;
+  if (!out_rgb) return fail(LR_ERR_INVALID, "out_rgb is null");
+  if (int rc = ensure_device()) return rc;
+  const size_t n = (size_t)dp.crop_w * dp.crop_h * 3;
+  float *d_sum = nullptr, *d_sq = nullptr;
+  LR_CUDA(cudaMalloc((void**)&d_sum, n * sizeof(float)));
+  int rc = LR_OK;
+  do {
+    if (cudaMemsetAsync(d_sum, 0, n * sizeof(float), 0) != cudaSuccess) { rc = fail(LR_ERR_CUDA, "cudaMemsetAsync failed"); break; }
+    if (out_sumsq) {
+      if (cudaMalloc((void**)&d_sq, n * sizeof(float)) != cudaSuccess) { rc = fail(LR_ERR_CUDA, "cudaMalloc(sumsq) failed"); break; }
+      if (cudaMemsetAsync(d_sq, 0, n * sizeof(float), 0) != cudaSuccess) { rc = fail(LR_ERR_CUDA, "cudaMemsetAsync failed"); break; }
+    }
+    LrStats dummy;
+    if (stats == nullptr) stats = &dummy;
+    // drop counters of earlier accumulate calls so the stats describe this call only
+    if ((rc = lr_stats_fetch(s, nullptr, stats)) != LR_OK) break;
+    if ((rc = lr_render_accumulate_device(s, p, d_sum, d_sq, nullptr)) != LR_OK) break;
+    cudaError_t e = launch_scale(d_sum, n, (float)dp.spp_count, 0);     // main.rs:104
+    if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("scale: ") + cudaGetErrorString(e)); break; }
+    if ((rc = lr_stats_fetch(s, nullptr, stats)) != LR_OK) break;
+    stats->launches += 1;
+    e = cudaMemcpy(out_rgb, d_sum, n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out_sumsq) e = cudaMemcpy(out_sumsq, d_sq, n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(e)); break; }
+  } while (0);
+  cudaFree(d_sum);
+  if (d_sq) cudaFree(d_sq);
+  return rc;
+}
+
+int lr_trace_primary(const LrScene* s, float u, float v, float ua, float va, int32_t* prim, float* t) {
+  if (!s || !prim || !t) return fail(LR_ERR_INVALID, "null argument");
+  if (int rc = ensure_device()) return rc;
+  const size_t n = (size_t)s->width * s->height;
+  int* d_prim = nullptr; float* d_t = nullptr;
+  LR_CUDA(cudaMalloc((void**)&d_prim, n * sizeof(int)));
+  cudaError_t e = cudaMalloc((void**)&d_t, n * sizeof(float));
+  if (e == cudaSuccess) e = launch_primary(s->dev, u, v, ua, va, d_prim, d_t, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(prim, d_prim, n * sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(t, d_t, n * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(d_prim);
+  if (d_t) cudaFree(d_t);
+  if (e != cudaSuccess) return fail(LR_ERR_CUDA, std::string("trace_primary: ") + cudaGetErrorString(e));
+  return LR_OK;
+}
+
+int lr_trace_rays(const LrScene* s, int64_t n, const float* origins, const float* directions, int32_t* prim, float* t, float* normal) {
+  if (!s || !origins || !directions || !prim || !t || n < 0) return fail(LR_ERR_INVALID, "bad argument");
+  if (n == 0) return LR_OK;
+  if (int rc = ensure_device()) return rc;
+  float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr, *d_n = nullptr; int* d_p = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d_o, n * 3 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_d, n * 3 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_t, n * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_p, n * sizeof(int));
+  if (e == cudaSuccess && normal) e = cudaMalloc((void**)&d_n, n * 3 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(d_o, origins, n * 3 * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_d, directions, n * 3 * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_rays(s->dev, n, d_o, d_d, d_p, d_t, d_n, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(prim, d_p, n * sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(t, d_t, n * sizeof(float), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && normal) e = cudaMemcpy(normal, d_n, n * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_p); if (d_n) cudaFree(d_n);
+  if (e != cudaSuccess) return fail(LR_ERR_CUDA, std::string("trace_rays: ") + cudaGetErrorString(e));
+  return LR_OK;
+}
+
+static int measure_read(uint64_t bytes, int iters, int warm, float* gbs) {
+  if (!gbs || bytes < (1u << 20) || iters <= 0) return fail(LR_ERR_INVALID, "bad argument");
+  if (int rc = ensure_device()) return rc;
+  const size_t n4 = bytes / 16;
+  float4* buf = nullptr; float* sink = nullptr;
+  LR_CUDA(cudaMalloc((void**)&buf, n4 * 16));
+  cudaError_t e = cudaMalloc((void**)&sink, 4);
+  if (e == cudaSuccess) e = cudaMemset(buf, 0, n4 * 16);
+  cudaEvent_t a = nullptr, b = nullptr;
+  if (e == cudaSuccess) e = cudaEventCreate(&a);
+  if (e == cudaSuccess) e = cudaEventCreate(&b);
+  const int blocks = std::max(g_sm_count, 1) * 8;
+  float best = 0.0f;
+  for (int rep = 0; rep < 5 && e == cudaSuccess; rep++) {
+    e = launch_read_bw(buf, n4, warm, blocks, sink, 0);                 // warm the cache level under test
+    if (e == cudaSuccess) e = cudaEventRecord(a, 0);
+    if (e == cudaSuccess) e = launch_read_bw(buf, n4, iters, blocks, sink, 0);
+    if (e == cudaSuccess) e = cudaEventRecord(b, 0);
+    if (e == cudaSuccess) e = cudaEventSynchronize(b);
+    float ms = 0.0f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, a, b);
+    if (e == cudaSuccess && ms > 0.0f) best = std::max(best, (float)((double)n4 * 16.0 * iters / (ms * 1e-3) / 1e9));
+  }
+  if (a) cudaEventDestroy(a);
+  if (b) cudaEventDestroy(b);
+  cudaFree(buf);
+  if (sink) cudaFree(sink);
+  if (e != cudaSuccess) return fail(LR_ERR_CUDA, std::string("measure_read: ") + cudaGetErrorString(e));
+  *gbs = best;
+  return LR_OK;
+}
+
+int lr_measure_l2_read_gbs(uint64_t working_set_bytes, int iters, float* gbs) { return measure_read(working_set_bytes, iters, 2, gbs); }
+int lr_measure_hbm_read_gbs(uint64_t bytes, int iters, float* gbs) { return measure_read(bytes, iters, 1, gbs); }
+
+}  // extern "C"

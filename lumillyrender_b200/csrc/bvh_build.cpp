@@ -1,0 +1,232 @@
+// bvh_build.cpp — host SAH BVH build + flattening to the 64-byte two-child node the kernels read.
+//
+// Replaces BVH::new / BVH::construct (src/bvh.rs:57-127).  The reference's full-sweep SAH with one
+// primitive per leaf is O(n log^2 n) and produces 2N-1 boxed nodes; the nearest hit does not depend
+// on the topology (device_path.cuh), so this build is free to differ: binned SAH (16 bins x 3 axes,
+// same cost model T_aabb = 1, T_tri = 2 as bvh.rs:71-72), leaves of up to 4 triangles (8 at most),
+// child boxes stored in the parent and padded outward so the device's node test is conservative,
+// nodes emitted in depth-first order (a node's near child is usually the next node in memory).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.h"
+#include "host_scene.h"
+
+namespace lr {
+
+namespace {
+
+struct Box {
+  float lo[3], hi[3];
+  void reset() { for (int i = 0; i < 3; i++) { lo[i] = INFINITY; hi[i] = -INFINITY; } }
+  void grow(const float* p) { for (int i = 0; i < 3; i++) { lo[i] = std::fmin(lo[i], p[i]); hi[i] = std::fmax(hi[i], p[i]); } }
+  void grow(const Box& b) { for (int i = 0; i < 3; i++) { lo[i] = std::fmin(lo[i], b.lo[i]); hi[i] = std::fmax(hi[i], b.hi[i]); } }
+  float area() const {
+    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return 2.0f * (dx * dy + dy * dz + dz * dx);
+  }
+};
+
+constexpr int kBins = 16;
+constexpr int kLeafTarget = 4;     // stop splitting at <= 4 triangles
+constexpr int kLeafMax = 8;        // leaf code holds count-1 in 3 bits
+constexpr int kSahDepthLimit = 32; // deeper than this: median splits only, so depth <= 32 + log2(n) < 64
+
+struct Builder {
+  const std::vector<Box>& tri_box;
+  const std::vector<Vec3>& centroid;
+  std::vector<int>& order;           // permutation being partitioned in place
+  std::vector<LrBvhNode> nodes;
+  int max_depth = 0;
+  float pad = 0.0f;
+
+  Box bounds(int begin, int end) const {
+    Box b; b.reset();
+    for (int i = begin; i < end; i++) b.grow(tri_box[order[i]]);
+    return b;
+  }
+
+  static int leaf_code(int first, int count) { return ~((first << 3) | (count - 1)); }
+
+  void store_child(LrBvhNode& n, int slot, const Box& b, int code, int count) {
+    for (int i = 0; i < 3; i++) {
+      n.f[slot * 6 + i] = b.lo[i] - pad;
+      n.f[slot * 6 + 3 + i] = b.hi[i] + pad;
+    }
+    n.c[slot] = code;
+    n.n[slot] = count;
+  }
+
+  // picks a partition of [begin,end); returns mid (begin < mid < end)
+  int partition(int begin, int end, const Box& node_box, int depth) {
+    const int n = end - begin;
+    Box cb; cb.reset();
+    for (int i = begin; i < end; i++) cb.grow(centroid[order[i]].v);
+    int best_axis = -1, best_bin = -1;
+    float best_cost = INFINITY;
+    if (depth < kSahDepthLimit) {
+      const float parent_area = node_box.area();
+      for (int axis = 0; axis < 3; axis++) {
+        const float ext = cb.hi[axis] - cb.lo[axis];
+        if (!(ext > 0.0f)) continue;
+        Box bin_box[kBins]; int bin_n[kBins];
+        for (int b = 0; b < kBins; b++) { bin_box[b].reset(); bin_n[b] = 0; }
+        const float scale = (float)kBins / ext;
+        for (int i = begin; i < end; i++) {
+          int b = (int)((centroid[order[i]][axis] - cb.lo[axis]) * scale);
+          b = std::min(std::max(b, 0), kBins - 1);
+          bin_box[b].grow(tri_box[order[i]]); bin_n[b]++;
+        }
+        float right_area[kBins]; int right_n[kBins];
+        Box acc; acc.reset(); int cnt = 0;
+        for (int b = kBins - 1; b > 0; b--) { acc.grow(bin_box[b]); cnt += bin_n[b]; right_area[b] = acc.area(); right_n[b] = cnt; }
+        acc.reset(); cnt = 0;
+        for (int b = 0; b + 1 < kBins; b++) {
+          acc.grow(bin_box[b]); cnt += bin_n[b];
+          if (cnt == 0 || right_n[b + 1] == 0) continue;
+          // bvh.rs:107: T = 2*T_aabb + (A(S1)*N(S1) + A(S2)*N(S2)) * T_tri / A(S)
+          const float cost = 2.0f * 1.0f + (acc.area() * (float)cnt + right_area[b + 1] * (float)right_n[b + 1]) * 2.0f / parent_area;
+          if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+        }
+      }
+    }
+    if (best_axis >= 0) {
+      const float ext = cb.hi[best_axis] - cb.lo[best_axis];
+      const float scale = (float)kBins / ext;
+      const float lo = cb.lo[best_axis];
+      const int axis = best_axis, bin = best_bin;
+      auto it = std::partition(order.begin() + begin, order.begin() + end, [&](int t) {
+        int b = (int)((centroid[t][axis] - lo) * scale);
+        b = std::min(std::max(b, 0), kBins - 1);
+        return b <= bin;
+      });
+      const int mid = (int)(it - order.begin());
+      if (mid > begin && mid < end) return mid;
+    }
+    // median split along the widest centroid axis (also the bounded-depth fallback)
+    int axis = 0;
+    for (int a = 1; a < 3; a++) if (cb.hi[a] - cb.lo[a] > cb.hi[axis] - cb.lo[axis]) axis = a;
+    const int mid = begin + n / 2;
+    std::nth_element(order.begin() + begin, order.begin() + mid, order.begin() + end,
+                     [&](int a, int b) { return centroid[a][axis] < centroid[b][axis]; });
+    return mid;
+  }
+
+  // builds the inner node covering [begin,end) (n >= 2) and returns its index
+  int build_inner(int begin, int end, const Box& box, int depth) {
+    max_depth = std::max(max_depth, depth + 1);
+    const int me = (int)nodes.size();
+    nodes.push_back(LrBvhNode{});
+    const int mid = partition(begin, end, box, depth);
+    const int range[2][2] = {{begin, mid}, {mid, end}};
+    for (int slot = 0; slot < 2; slot++) {
+      const int b = range[slot][0], e = range[slot][1], cnt = e - b;
+      const Box cbx = bounds(b, e);
+      bool leaf = cnt <= kLeafTarget;
+      if (!leaf && cnt <= kLeafMax && depth + 1 >= kStackGuardDepth) leaf = true;
+      if (leaf) {
+        LrBvhNode tmp = nodes[me]; store_child(tmp, slot, cbx, leaf_code(b, cnt), cnt); nodes[me] = tmp;
+      } else {
+        const int child = build_inner(b, e, cbx, depth + 1);
+        LrBvhNode tmp = nodes[me]; store_child(tmp, slot, cbx, child, 0); nodes[me] = tmp;
+      }
+    }
+    return me;
+  }
+
+  static constexpr int kStackGuardDepth = 60;
+};
+
+}  // namespace
+
+int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, int& depth_out, float& seconds_out) {
+  const auto t0 = std::chrono::steady_clock::now();
+  nodes_out.clear();
+  depth_out = 0;
+  seconds_out = 0.0f;
+  const int n = (int)tris.size();
+  if (n == 0) return LR_OK;
+  if (n >= (1 << 28)) return fail(LR_ERR_UNSUPPORTED, "more than 2^28 triangles");
+  std::vector<Box> tri_box(n);
+  std::vector<Vec3> centroid(n);
+  std::vector<int> order(n);
+  Box all; all.reset();
+  for (int i = 0; i < n; i++) {
+    Box b; b.reset();
+    b.grow(tris[i].p0); b.grow(tris[i].p1); b.grow(tris[i].p2);
+    for (int k = 0; k < 3; k++)
+      if (!std::isfinite(b.lo[k]) || !std::isfinite(b.hi[k])) return fail(LR_ERR_INVALID, "non-finite triangle vertex");
+    tri_box[i] = b;
+    centroid[i] = vec3(0.5f * (b.lo[0] + b.hi[0]), 0.5f * (b.lo[1] + b.hi[1]), 0.5f * (b.lo[2] + b.hi[2]));
+    order[i] = i;
+    all.grow(b);
+  }
+  Builder bld{tri_box, centroid, order, {}, 0, 0.0f};
+  float extent = 0.0f;
+  for (int k = 0; k < 3; k++) extent = std::fmax(extent, std::fmax(std::fabs(all.lo[k]), std::fabs(all.hi[k])));
+  bld.pad = 4e-6f * extent + 1e-30f;     // > the rounding error of (box - origin) * inv, see device_path.cuh
+  bld.nodes.reserve((size_t)n / 2 + 16);
+  if (n == 1) {
+    // a single leaf: both children reference it (testing a triangle twice cannot change the minimum)
+    LrBvhNode root{};
+    bld.store_child(root, 0, all, Builder::leaf_code(0, 1), 1);
+    bld.store_child(root, 1, all, Builder::leaf_code(0, 1), 1);
+    bld.nodes.push_back(root);
+    bld.max_depth = 1;
+  } else {
+    bld.build_inner(0, n, all, 0);
+  }
+  std::vector<LrTriangle> permuted(n);
+  for (int i = 0; i < n; i++) permuted[i] = tris[order[i]];
+  tris.swap(permuted);
+  nodes_out.swap(bld.nodes);
+  depth_out = bld.max_depth;
+  seconds_out = std::chrono::duration<float>(std::chrono::steady_clock::now() - t0).count();
+  return LR_OK;
+}
+
+// Structural validation of a description handed over the C ABI (the reference panics instead).
+int validate_desc(const LrSceneDesc& d) {
+  if (d.n_materials < 0 || d.n_triangles < 0 || d.n_spheres < 0 || d.n_nodes < 0) return fail(LR_ERR_INVALID, "negative count");
+  if ((d.n_materials > 0 && !d.materials) || (d.n_triangles > 0 && !d.triangles) || (d.n_spheres > 0 && !d.spheres) || (d.n_nodes > 0 && !d.nodes))
+    return fail(LR_ERR_INVALID, "null array with non-zero count");
+  if ((d.n_triangles > 0) != (d.n_nodes > 0)) return fail(LR_ERR_INVALID, "BVH nodes must be present iff triangles are present (use lr_bvh_build / lr_host_scene_from_arrays)");
+  if (d.bvh_depth >= 64) return fail(LR_ERR_UNSUPPORTED, "BVH deeper than the device traversal stack (64)");
+  const int n_prims = d.n_triangles + d.n_spheres;
+  for (int i = 0; i < d.n_materials; i++)
+    if (d.materials[i].type < LR_MAT_LAMBERT || d.materials[i].type > LR_MAT_IDEAL_REFRACTION) return fail(LR_ERR_INVALID, "unknown material type");
+  for (int i = 0; i < d.n_triangles; i++) {
+    const LrTriangle& t = d.triangles[i];
+    if (t.material < 0 || t.material >= d.n_materials) return fail(LR_ERR_INVALID, "triangle material index out of range");
+    if (t.prim_id < 0 || t.prim_id >= n_prims) return fail(LR_ERR_INVALID, "triangle prim_id out of range");
+  }
+  for (int i = 0; i < d.n_spheres; i++) {
+    const LrSphere& s = d.spheres[i];
+    if (s.material < 0 || s.material >= d.n_materials) return fail(LR_ERR_INVALID, "sphere material index out of range");
+    if (s.prim_id < 0 || s.prim_id >= n_prims) return fail(LR_ERR_INVALID, "sphere prim_id out of range");
+  }
+  for (int i = 0; i < d.n_nodes; i++) {
+    for (int k = 0; k < 2; k++) {
+      const int c = d.nodes[i].c[k];
+      if (c >= 0) { if (c >= d.n_nodes) return fail(LR_ERR_INVALID, "BVH child index out of range"); }
+      else {
+        const int code = ~c, first = code >> 3, count = (code & 7) + 1;
+        if (first < 0 || first + count > d.n_triangles) return fail(LR_ERR_INVALID, "BVH leaf range out of bounds");
+      }
+    }
+  }
+  const LrCamera& c = d.camera;
+  if (c.type < LR_CAM_IDEAL_PINHOLE || c.type > LR_CAM_OMNIDIRECTIONAL) return fail(LR_ERR_INVALID, "unknown camera type");
+  if (c.width <= 0 || c.height <= 0) return fail(LR_ERR_INVALID, "camera resolution must be positive");
+  if ((int64_t)c.width * c.height >= (1LL << 31)) return fail(LR_ERR_UNSUPPORTED, "film larger than 2^31 pixels");
+  if (d.sky.type == LR_SKY_IBL) {
+    if (!d.sky.pixels || d.sky.height <= 0) return fail(LR_ERR_INVALID, "IBL sky without pixels");
+    if (d.sky.n_pixels < 2LL * d.sky.height * d.sky.height) return fail(LR_ERR_INVALID, "IBL sky: n_pixels < 2*height*height (sky.rs:64-72 indexes a 2H x H image)");
+  } else if (d.sky.type != LR_SKY_UNIFORM) return fail(LR_ERR_INVALID, "unknown sky type");
+  return LR_OK;
+}
+
+}  // namespace lr

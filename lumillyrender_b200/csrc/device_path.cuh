@@ -1,0 +1,521 @@
+// device_path.cuh — device-side building blocks of the path-tracing hot path (sm_100a).
+//
+// NUMERICS CONTRACT.  This translation unit is compiled with -fmad=false, IEEE division and
+// square root (-prec-div=true -prec-sqrt=true, no fast-math), so every expression below rounds
+// exactly like the reference's fp32 code compiled by rustc without FMA (README.md:12,
+// SURVEY.md §7 hard part 1).  The BVH *node* slab test uses the cancellation-safe
+// (box - origin) * inv form on boxes the host padded outward; it is a conservative cull and
+// never decides a hit.  A hit is decided only by (a) the reference's primitive test (triangle.rs:69-100,
+// sphere.rs:42-63) and (b) the reference's slab test on the primitive's own AABB
+// (aabb.rs:75-92 as applied by Leaf::may_intersect, bvh.rs:21-25), so the nearest hit equals
+// the reference's regardless of BVH topology.
+#pragma once
+#include "device_scene.h"
+
+namespace lr {
+
+#define LR_DEV __device__ __forceinline__
+
+constexpr float kPI = 3.14159265358979323846264338327950288f;   // constant.rs:1
+constexpr float kEPS = 1e-3f;                                   // constant.rs:2
+constexpr float kINF = 1e5f;                                    // constant.rs:3
+
+// ------------------------------------------------------------------ vector math (math/vector3.rs)
+struct F3 { float x, y, z; };
+LR_DEV F3 f3(float x, float y, float z) { F3 r; r.x = x; r.y = y; r.z = z; return r; }
+LR_DEV F3 f3(const float* p) { return f3(p[0], p[1], p[2]); }
+LR_DEV F3 f3(float4 v) { return f3(v.x, v.y, v.z); }
+LR_DEV F3 operator-(F3 a) { return f3(-a.x, -a.y, -a.z); }
+LR_DEV F3 operator+(F3 a, F3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+LR_DEV F3 operator-(F3 a, F3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+LR_DEV F3 operator*(F3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+LR_DEV F3 operator*(float s, F3 a) { return f3(s * a.x, s * a.y, s * a.z); }
+LR_DEV F3 operator*(F3 a, F3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+LR_DEV F3 operator/(F3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+LR_DEV float dot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+LR_DEV F3 cross(F3 a, F3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+LR_DEV float sqr_norm(F3 a) { return dot(a, a); }
+LR_DEV float norm(F3 a) { return sqrtf(sqr_norm(a)); }
+LR_DEV F3 normalize(F3 a) { return a / norm(a); }            // three true divisions (traits.rs:38-42)
+LR_DEV float comp(F3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+// ------------------------------------------------------------------ RNG (replaces rand::random)
+// Counter-based: the stream of a sample is a pure function of (seed, pixel, sample index), so any
+// GPU can render any sample range and reproduce it bit for bit.  PCG32 (XSH-RR 64/32) stepped from
+// a splitmix64-hashed start; floats are (u32 >> 8) * 2^-24 in [0,1) like rand 0.3's f32.
+LR_DEV unsigned long long splitmix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+struct Pcg {
+  unsigned long long state;
+  LR_DEV unsigned int next_u32() {
+    const unsigned long long old = state;
+    state = old * 6364136223846793005ULL + 1442695040888963407ULL;
+    const unsigned int xorshifted = (unsigned int)(((old >> 18u) ^ old) >> 27u);
+    const unsigned int rot = (unsigned int)(old >> 59u);
+    return __funnelshift_r(xorshifted, xorshifted, rot);
+  }
+  LR_DEV float next() { return (float)(next_u32() >> 8) * (1.0f / 16777216.0f); }
+  LR_DEV void seed(unsigned long long seed, unsigned int pixel, unsigned int sample) {
+    state = splitmix64(splitmix64(seed + 0x632BE59BD9B4E019ULL * (unsigned long long)pixel) ^
+                       ((unsigned long long)sample * 0xD1B54A32D192ED03ULL));
+    next_u32();
+  }
+};
+
+// ------------------------------------------------------------------ reference slab test (aabb.rs:75-92)
+// inv = 1.0f / direction (the same IEEE quotient the reference recomputes at every node)
+LR_DEV bool ref_slab_pass(F3 lo, F3 hi, F3 o, F3 inv) {
+  float mn = -kINF, mx = kINF;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const float t1 = (comp(lo, i) - comp(o, i)) * comp(inv, i);
+    const float t2 = (comp(hi, i) - comp(o, i)) * comp(inv, i);
+    float t_min, t_max;
+    if (t1 > t2) { t_min = t2; t_max = t1; } else { t_min = t1; t_max = t2; }
+    if (mn < t_min) mn = t_min;
+    if (mx > t_max) mx = t_max;
+    if (mn > mx) return false;
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------ primitive tests
+// triangle.rs:69-100.  Returns t or a negative value for a miss.
+LR_DEV float triangle_mt(F3 p0, F3 p1, F3 p2, F3 o, F3 d) {
+  const F3 e1 = p1 - p0;
+  const F3 e2 = p2 - p0;
+  const F3 pv = cross(d, e2);
+  const float det = dot(e1, pv);
+  if (fabsf(det) < kEPS) return -1.0f;
+  const float invdet = 1.0f / det;
+  const F3 tv = o - p0;
+  const float u = dot(tv, pv) * invdet;
+  if (u < 0.0f || u > 1.0f) return -1.0f;
+  const F3 qv = cross(tv, e1);
+  const float v = dot(d, qv) * invdet;
+  if (v < 0.0f || u + v > 1.0f) return -1.0f;
+  const float t = dot(e2, qv) * invdet;
+  if (!(t >= kEPS)) return -1.0f;      // `t < EPS` rejects; a NaN t (reference: panic) is a miss
+  return t;
+}
+// sphere.rs:42-56.  Returns t or a negative value for a miss.
+LR_DEV float sphere_hit(F3 c, float r, F3 o, F3 d) {
+  const F3 co = o - c;
+  const float cod = dot(co, d);
+  const float det = cod * cod - sqr_norm(co) + r * r;
+  if (!(det > 0.0f)) return -1.0f;
+  const float sq = sqrtf(det);
+  const float t1 = -cod - sq;
+  const float t2 = -cod + sq;
+  if (t1 < kEPS && t2 < kEPS) return -1.0f;
+  const float t = t1 > kEPS ? t1 : t2;
+  if (!(t == t)) return -1.0f;
+  return t;
+}
+
+struct TraceCounters { unsigned int nodes, tris, spheres; };
+
+LR_DEV float4 ldg4(const float4* p) { return __ldg(p); }
+
+// Nearest hit.  id: -1 miss, >= 0 triangle index (leaf order), <= -2 sphere index = -2 - id.
+// Spheres are tested first by a flat loop (exact reference arithmetic, no culling at all: the
+// r = 1e5 ground sphere of scenes/primitive.toml has a t error far larger than any box slack).
+template <bool COUNT>
+LR_DEV void trace(const DevScene& sc, F3 o, F3 d, float& t_out, int& id_out, TraceCounters& tc) {
+  const F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+  float best_t = 3.0e38f;
+  int best = -1;
+
+  for (int i = 0; i < sc.n_spheres; i++) {
+    const float4 s = ldg4(sc.spheres + i);
+    if (COUNT) tc.spheres++;
+    const float t = sphere_hit(f3(s), s.w, o, d);
+    if (t >= 0.0f && t < best_t) {
+      const F3 c = f3(s);
+      const F3 r = f3(s.w, s.w, s.w);
+      if (ref_slab_pass(c - r, c + r, o, inv)) { best_t = t; best = -2 - i; }
+    }
+  }
+
+  if (sc.n_nodes > 0) {
+    // conservative cull distance: a primitive's computed t may precede its box's computed entry
+    float cull_t = best_t < 3.0e38f ? best_t * 1.0001f + 1e-4f : 3.0e38f;
+    int stack[kStackDepth];
+    int sp = 0;
+    int cur = 0;
+    while (true) {
+      if (cur >= 0) {
+        const float4* np = sc.nodes + 4 * (size_t)cur;
+        const float4 n0 = ldg4(np + 0), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
+        if (COUNT) tc.nodes++;
+        // child 0: lo = (n0.x,n0.y,n0.z) hi = (n0.w,n1.x,n1.y); child 1: lo = (n1.z,n1.w,n2.x) hi = (n2.y,n2.z,n2.w)
+        const float ax0 = (n0.x - o.x) * inv.x, bx0 = (n0.w - o.x) * inv.x;
+        const float ay0 = (n0.y - o.y) * inv.y, by0 = (n1.x - o.y) * inv.y;
+        const float az0 = (n0.z - o.z) * inv.z, bz0 = (n1.y - o.z) * inv.z;
+        const float ax1 = (n1.z - o.x) * inv.x, bx1 = (n2.y - o.x) * inv.x;
+        const float ay1 = (n1.w - o.y) * inv.y, by1 = (n2.z - o.y) * inv.y;
+        const float az1 = (n2.x - o.z) * inv.z, bz1 = (n2.w - o.z) * inv.z;
+        const float en0 = fmaxf(fmaxf(fminf(ax0, bx0), fminf(ay0, by0)), fmaxf(fminf(az0, bz0), 0.0f));
+        const float ex0 = fminf(fminf(fmaxf(ax0, bx0), fmaxf(ay0, by0)), fminf(fmaxf(az0, bz0), cull_t));
+        const float en1 = fmaxf(fmaxf(fminf(ax1, bx1), fminf(ay1, by1)), fmaxf(fminf(az1, bz1), 0.0f));
+        const float ex1 = fminf(fminf(fmaxf(ax1, bx1), fmaxf(ay1, by1)), fminf(fmaxf(az1, bz1), cull_t));
+        const bool h0 = en0 <= ex0, h1 = en1 <= ex1;
+        const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+        if (h0 && h1) {
+          const bool first0 = en0 <= en1;
+          stack[sp++] = first0 ? c1 : c0;
+          cur = first0 ? c0 : c1;
+          continue;
+        }
+        if (h0) { cur = c0; continue; }
+        if (h1) { cur = c1; continue; }
+      } else {
+        const int code = ~cur;
+        const int first = code >> 3;
+        const int count = (code & 7) + 1;
+        for (int k = 0; k < count; k++) {
+          const float4* tp = sc.tris + 3 * (size_t)(first + k);
+          const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
+          if (COUNT) tc.tris++;
+          const F3 p0 = f3(v0), p1 = f3(v1), p2 = f3(v2);
+          const float t = triangle_mt(p0, p1, p2, o, d);
+          if (t >= 0.0f && t < best_t) {
+            // the leaf's own AABB gate (triangle.rs:102-119 box, aabb.rs:75-92 test)
+            const F3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
+            const F3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
+            if (ref_slab_pass(lo, hi, o, inv)) {
+              best_t = t;
+              best = first + k;
+              cull_t = best_t * 1.0001f + 1e-4f;
+            }
+          }
+        }
+      }
+      if (sp == 0) break;
+      cur = stack[--sp];
+    }
+  }
+  t_out = best_t;
+  id_out = best;
+}
+
+struct Surface {
+  F3 pos, n;
+  int mat, prim;
+};
+
+// Intersection record of the nearest hit (triangle.rs:93-99, sphere.rs:55-62)
+LR_DEV Surface surface_at(const DevScene& sc, F3 o, F3 d, float t, int id) {
+  Surface s;
+  s.pos = o + d * t;
+  if (id >= 0) {
+    const float4* tp = sc.tris + 3 * (size_t)id;
+    const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
+    const F3 p0 = f3(v0), p1 = f3(v1), p2 = f3(v2);
+    s.n = normalize(cross(p1 - p0, p2 - p0));          // triangle.rs:36
+    s.prim = __float_as_int(v0.w);
+    s.mat = __float_as_int(v1.w);
+  } else {
+    const int i = -2 - id;
+    const float4 sp = ldg4(sc.spheres + i);
+    const int2 meta = __ldg(sc.sphere_meta + i);
+    s.n = normalize(s.pos - f3(sp));                   // sphere.rs:56
+    s.mat = meta.x;
+    s.prim = meta.y;
+  }
+  return s;
+}
+
+// ------------------------------------------------------------------ sampling utilities (util.rs)
+LR_DEV void orthonormal_basis(F3 n, F3& tangent, F3& binormal) {   // util.rs:12-21
+  const F3 a = fabsf(n.x) > kEPS ? f3(0.0f, 1.0f, 0.0f) : f3(1.0f, 0.0f, 0.0f);
+  tangent = normalize(cross(a, n));
+  binormal = cross(n, tangent);
+}
+LR_DEV F3 reflect(F3 v, F3 normal) { return -v + normal * (dot(v, normal) * 2.0f); }   // util.rs:30-32
+LR_DEV bool refract(F3 v, F3 normal, float eta, F3& out) {                               // util.rs:34-42
+  const float dn = dot(v, normal);
+  const float cos2theta = 1.0f - (eta * eta) * (1.0f - dn * dn);
+  if (cos2theta > 0.0f) {
+    out = -v * eta - normal * (eta * -dn + sqrtf(cos2theta));
+    return true;
+  }
+  return false;
+}
+LR_DEV F3 orienting_normal(F3 out_, F3 normal) {                   // lambert.rs:14-21
+  if (dot(normal, out_) < 0.0f) return normal * -1.0f;
+  return normal;
+}
+
+// ------------------------------------------------------------------ materials
+struct Mat {
+  F3 color; int type;
+  F3 emission; float param0;
+  float param1, weight; bool emissive;
+};
+LR_DEV Mat load_mat(const DevScene& sc, int i) {
+  const float4 a = ldg4(sc.mats + 3 * i), b = ldg4(sc.mats + 3 * i + 1), c = ldg4(sc.mats + 3 * i + 2);
+  Mat m;
+  m.color = f3(a); m.type = __float_as_int(a.w);
+  m.emission = f3(b); m.param0 = b.w;
+  m.param1 = c.x; m.weight = c.y; m.emissive = c.z != 0.0f;
+  return m;
+}
+
+LR_DEV float signed_mod(float base, float module) {                // lambert.rs:58-64
+  if (base > 0.0f) return fmodf(base, module);
+  return module - fmodf(-base, module);
+}
+LR_DEV float checker(float u, float v) {                           // lambert.rs:66-90 (grey value)
+  const float lw = 2.0f, li = 150.0f, sw = 1.0f, si = 30.0f, cw = 150.0f, ci = 300.0f;
+  const float lu = signed_mod(u, li), lv = signed_mod(v, li);
+  if (lu < lw || lv < lw) return 0.5f;
+  const float su = signed_mod(u, si), sv = signed_mod(v, si);
+  if (su < sw || sv < sw) return 0.6f;
+  const float cu = signed_mod(u, ci), cv = signed_mod(v, ci);
+  if ((cu < cw || cv < cw) && !(cu < cw && cv < cw)) return 0.8f;
+  return 1.0f;
+}
+LR_DEV float powi5(float x) { const float x2 = x * x; const float x4 = x2 * x2; return x * x4; }   // llvm.powi(x, 5)
+
+LR_DEV float ggx_g1(float a2, F3 v, F3 n) {                        // ggx.rs:27-32
+  const float c = dot(v, n);
+  const float tan = 1.0f / (c * c) - 1.0f;
+  return 2.0f / (1.0f + sqrtf(1.0f + a2 * tan * tan));
+}
+LR_DEV float ggx_ndf(float a2, F3 m, F3 n) {                       // ggx.rs:34-39
+  const float mdn = dot(m, n);
+  const float x = (a2 - 1.0f) * mdn * mdn + 1.0f;
+  return a2 / (kPI * x * x);
+}
+LR_DEV void ior_pair(const Mat& m, F3 out_, F3 n, float& from_ior, float& to_ior) {   // ideal_refraction.rs:117-135
+  if (dot(out_, n) > 0.0f) { from_ior = 1.0f; to_ior = m.param1; } else { from_ior = m.param1; to_ior = 1.0f; }
+}
+LR_DEV float fresnel_exact(float n1, float n2, F3 out_, F3 in_, F3 on) {               // ideal_refraction.rs:137-147
+  const float cos1 = dot(out_, on);
+  const float cos2 = dot(in_, -on);
+  const float a = (n1 * cos1 - n2 * cos2) / (n1 * cos1 + n2 * cos2);
+  const float b = (n1 * cos2 - n2 * cos1) / (n1 * cos2 + n2 * cos1);
+  return (a * a + b * b) / 2.0f;
+}
+
+// Material::brdf
+LR_DEV F3 mat_brdf(const Mat& m, F3 out_, F3 in_, F3 n, F3 pos) {
+  switch (m.type) {
+    case LR_MAT_LAMBERT: {                                         // lambert.rs:32-35
+      const float c = checker(pos.x, pos.z);
+      return m.color * f3(c, c, c) / kPI;
+    }
+    case LR_MAT_PHONG: {                                           // phong.rs:39-47
+      const F3 on = orienting_normal(out_, n);
+      if (dot(in_, on) <= 0.0f) return f3(0.0f, 0.0f, 0.0f);
+      const F3 r = reflect(out_, on);
+      const float c = dot(r, in_);
+      const float a = m.param0;
+      return m.color * ((a + 2.0f) / (2.0f * kPI) * powf(c, a));
+    }
+    case LR_MAT_BLINN_PHONG: {                                     // blinn_phong.rs:39-49
+      const F3 on = orienting_normal(out_, n);
+      if (dot(in_, on) <= 0.0f) return f3(0.0f, 0.0f, 0.0f);
+      const F3 h = normalize(in_ + out_);
+      const float c = dot(h, on);
+      const float a = m.param0;
+      return m.color * ((a + 2.0f) * (a + 4.0f) / (8.0f * kPI * (powf(2.0f, -a / 2.0f) + a)) * powf(c, a));
+    }
+    case LR_MAT_GGX: {                                             // ggx.rs:71-85
+      const F3 on = orienting_normal(out_, n);
+      if (dot(in_, on) <= 0.0f) return f3(0.0f, 0.0f, 0.0f);
+      const F3 h = normalize(in_ + out_);
+      const float alpha = m.param0 * m.param0;
+      const float a2 = alpha * alpha;
+      const float nnn = 1.0f - m.param1, nnp = 1.0f + m.param1;   // ggx.rs:41-47
+      const float f_0 = (nnn * nnn) / (nnp * nnp);
+      const float f = f_0 + (1.0f - f_0) * powi5(1.0f - dot(in_, h));
+      const float g = ggx_g1(a2, in_, on) * ggx_g1(a2, out_, on);
+      const float d = ggx_ndf(a2, h, on);
+      return m.color * f * g * d / (4.0f * dot(in_, on) * dot(out_, on));
+    }
+    default: {                                                     // ideal_refraction.rs:40-68
+      const F3 on = orienting_normal(out_, n);
+      float from_ior, to_ior;
+      ior_pair(m, out_, n, from_ior, to_ior);
+      F3 r;
+      if (refract(out_, on, from_ior / to_ior, r)) {
+        const float fr = fresnel_exact(from_ior, to_ior, out_, r, on);
+        if (dot(in_, on) > 0.0f) return m.color * 1.0f / dot(in_, n) * fr;
+        const float q = to_ior / from_ior;
+        const float ft = (1.0f - fr) * (q * q);
+        return m.color * 1.0f / dot(in_, n) * ft;
+      }
+      return m.color * 1.0f / dot(in_, n);
+    }
+  }
+}
+
+// Material::sample (draw order as the reference)
+LR_DEV void mat_sample(const Mat& m, F3 out_, F3 n, Pcg& rng, F3& in_, float& pdf) {
+  const F3 on = orienting_normal(out_, n);
+  if (m.type == LR_MAT_IDEAL_REFRACTION) {                         // ideal_refraction.rs:70-104
+    float from_ior, to_ior;
+    ior_pair(m, out_, n, from_ior, to_ior);
+    F3 r;
+    if (refract(out_, on, from_ior / to_ior, r)) {
+      const float fr = fresnel_exact(from_ior, to_ior, out_, r, on);
+      if (rng.next() < fr) { in_ = reflect(out_, on); pdf = 1.0f * fr; }
+      else { in_ = r; pdf = 1.0f * (1.0f - fr); }
+    } else { in_ = reflect(out_, on); pdf = 1.0f; }
+    return;
+  }
+  const float xi1 = rng.next();
+  const float xi2 = rng.next();
+  const float r1 = 2.0f * kPI * xi1;
+  float s1, c1;
+  sincosf(r1, &s1, &c1);
+  switch (m.type) {
+    case LR_MAT_LAMBERT: {                                         // lambert.rs:37-55 + util.rs:87-96
+      F3 u, v;
+      orthonormal_basis(on, u, v);
+      const float r2s = sqrtf(xi2);
+      const F3 s = f3(c1 * r2s, s1 * r2s, sqrtf(1.0f - xi2));
+      in_ = u * s.x + v * s.y + on * s.z;
+      pdf = dot(in_, n) / kPI;
+      return;
+    }
+    case LR_MAT_PHONG: {                                           // phong.rs:49-69
+      const float a = m.param0;
+      const F3 r = reflect(out_, on);
+      F3 u, v;
+      orthonormal_basis(r, u, v);
+      const float t = powf(xi2, 1.0f / (a + 2.0f));
+      const float ts = sqrtf(1.0f - t * t);
+      in_ = u * c1 * ts + v * s1 * ts + r * t;
+      pdf = (a + 2.0f) / (2.0f * kPI) * powf(dot(r, in_), a);
+      return;
+    }
+    case LR_MAT_BLINN_PHONG: {                                     // blinn_phong.rs:51-73
+      const float a = m.param0;
+      F3 u, v;
+      orthonormal_basis(on, u, v);
+      const float t = powf(xi2, 1.0f / (a + 2.0f));
+      const float ts = sqrtf(1.0f - t * t);
+      const F3 h = u * c1 * ts + v * s1 * ts + on * t;
+      in_ = h * (2.0f * dot(out_, h)) - out_;
+      pdf = (a + 2.0f) / (2.0f * kPI) * powf(dot(on, h), a);
+      return;
+    }
+    default: {                                                     // ggx.rs:87-113
+      F3 u, v;
+      orthonormal_basis(on, u, v);
+      const float alpha = m.param0 * m.param0;
+      const float a2 = alpha * alpha;
+      const float tan = alpha * sqrtf(xi2 / (1.0f - xi2));
+      const float x = 1.0f + tan * tan;
+      const float c = 1.0f / sqrtf(x);
+      const float s = tan / sqrtf(x);
+      const F3 h = u * c1 * s + v * s1 * s + on * c;
+      const float o_h = dot(out_, h);
+      in_ = h * (2.0f * o_h) - out_;
+      const float jacobian = 1.0f / (4.0f * o_h);
+      pdf = ggx_ndf(a2, h, on) * dot(h, on) * jacobian;
+      return;
+    }
+  }
+}
+
+// Material::coef (traits.rs:20-22; ideal_refraction.rs:106-113)
+LR_DEV F3 mat_coef(const Mat& m, F3 out_, F3 n, float fly_distance) {
+  if (m.type == LR_MAT_IDEAL_REFRACTION && dot(out_, n) < 0.0f) {
+    const F3 v = -(f3(1.0f, 1.0f, 1.0f) - m.color) * m.param0 * fly_distance;
+    return f3(expf(v.x), expf(v.y), expf(v.z));
+  }
+  return f3(1.0f, 1.0f, 1.0f);
+}
+
+// ------------------------------------------------------------------ sky (sky.rs)
+LR_DEV unsigned long long f32_to_usize(float v) {   // Rust `as usize`: saturating, NaN -> 0
+  if (!(v > 0.0f)) return 0ull;
+  if (v >= 1.8446744e19f) return 0xFFFFFFFFFFFFFFFFull;
+  return (unsigned long long)v;
+}
+LR_DEV F3 sky_radiance(const DevScene& sc, F3 d) {
+  if (sc.sky_type == LR_SKY_UNIFORM) return f3(sc.sky_color);      // sky.rs:17-21
+  const float theta = acosf(d.y);                                  // sky.rs:57-79
+  const float phi = atan2f(d.z, d.x);
+  const float u = fmodf((phi + kPI + sc.sky_longitude_offset) / (2.0f * kPI), 1.0f);
+  const float v = fmodf(theta / kPI, 1.0f);
+  const unsigned long long height = (unsigned long long)sc.sky_height;
+  const unsigned long long width = height * 2ull;
+  const unsigned long long all = width * height;
+  const unsigned long long x = f32_to_usize(floorf((float)width * u));
+  const unsigned long long y = f32_to_usize(floorf((float)height * v));
+  const unsigned long long index = y * width + x;
+  return f3(ldg4(sc.sky_pixels + (index % all)));
+}
+
+// ------------------------------------------------------------------ cameras (camera.rs)
+LR_DEV F3 cam_sensor_point(const LrCamera& c, int left, int top, float u, float v) {   // camera.rs:64-81
+  const float px = ((((float)left + u) / (float)c.width) - 0.5f) * c.sensor_size[0];
+  const float py = ((((float)top + v) / (float)c.height) - 0.5f) * c.sensor_size[1];
+  return f3(c.position) - f3(c.right) * px + f3(c.up) * py;
+}
+LR_DEV F3 cam_aperture_point(const LrCamera& c, float xi1, float xi2) {                // camera.rs:285-300
+  const float u = 2.0f * kPI * xi1;
+  const float v = sqrtf(xi2) * c.aperture_radius;
+  float su, cu;
+  sincosf(u, &su, &cu);
+  return f3(c.aperture_position) + f3(c.right) * (cu * v) + f3(c.up) * (su * v);
+}
+LR_DEV float cam_geometry_term(const LrCamera& c, F3 direction) {                      // camera.rs:302-309
+  const float cos_term = dot(direction, f3(c.forward));
+  const float d = c.aperture_sensor_distance / cos_term;
+  return cos_term * cos_term / (d * d);
+}
+// Returns the ray and the per-sample weight  g_term * (sensor_sensitivity / pdf)  (main.rs:99-101);
+// `draw` supplies the U[0,1) numbers in the reference's order: sensor u, v, then aperture 2.
+template <class Draw>
+LR_DEV void camera_sample(const LrCamera& c, int x, int y, Draw&& draw, F3& o, F3& d, float& g_term, float& sens_over_pdf) {
+  const float u = draw();
+  const float v = draw();
+  if (c.type == LR_CAM_IDEAL_PINHOLE) {                            // camera.rs:100-115
+    const F3 sensor = cam_sensor_point(c, x, y, u, v);
+    o = f3(c.aperture_position);
+    d = normalize(o - sensor);
+    g_term = 1.0f;
+    sens_over_pdf = c.sensor_sensitivity / (1.0f * 1.0f);
+  } else if (c.type == LR_CAM_OMNIDIRECTIONAL) {                   // camera.rs:168-188
+    const float p = ((float)x + u) / (float)c.width * kPI * 2.0f;
+    const float t = ((float)y + v) / (float)c.height * kPI;
+    float sp, cp, st, ct;
+    sincosf(p, &sp, &cp);
+    sincosf(t, &st, &ct);
+    o = f3(c.aperture_position);
+    d = f3(st * cp, st * sp, ct);
+    g_term = 1.0f;
+    sens_over_pdf = c.sensor_sensitivity / 1.0f;
+  } else {
+    const F3 sensor = cam_sensor_point(c, x, y, u, v);
+    const float sensor_pdf = 1.0f / c.sensor_pixel_area;
+    const float a1 = draw();
+    const float a2 = draw();
+    const F3 ap = cam_aperture_point(c, a1, a2);
+    const float ap_pdf = 1.0f / (kPI * c.aperture_radius * c.aperture_radius);
+    o = ap;
+    if (c.type == LR_CAM_PINHOLE) {                                // camera.rs:313-328
+      d = normalize(ap - sensor);
+      g_term = cam_geometry_term(c, d);
+    } else {                                                       // camera.rs:458-476
+      const F3 apc = f3(c.aperture_position);
+      const F3 sensor_center = apc - sensor;
+      const F3 object_plane = sensor_center * (c.focus_distance / dot(sensor_center, f3(c.forward)));
+      d = normalize(apc + object_plane - ap);
+      g_term = cam_geometry_term(c, normalize(ap - sensor));
+    }
+    sens_over_pdf = c.sensor_sensitivity / (sensor_pdf * ap_pdf);
+  }
+}
+
+}  // namespace lr

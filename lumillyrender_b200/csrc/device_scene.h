@@ -1,0 +1,52 @@
+// device_scene.h — layout of the scene in HBM and the kernel parameter blocks.
+//
+// Everything the kernels read is a flat, 16-byte aligned array so that every fetch on the
+// traversal path is a 128-bit load:
+//   nodes    : 4 x float4 per BVH node   (64 B)   — two child boxes + child codes
+//   tris     : 3 x float4 per triangle   (48 B)   — p0|prim_id, p1|material, p2|0   (BVH leaf order)
+//   spheres  : 1 x float4 per sphere     (16 B)   — centre|radius     (+ int2 material/prim_id)
+//   mats     : 3 x float4 per material   (48 B)   — colour|type, emission|param0, param1|weight|emissive|0
+//   emitters : 3 x float4 per emitter    (48 B)   — tri: p0|kind, p1|area, p2|0 ; sphere: centre|kind, radius,0,0|area
+//   sky      : 1 x float4 per texel (rgb|0), nearest-texel lookup
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/lumilly.h"
+
+namespace lr {
+
+constexpr int kStackDepth = 64;          // per-thread traversal stack entries
+constexpr int kBlockThreads = 128;       // 4 warps, each warp owns an 8x4 pixel tile
+
+struct DevScene {
+  const float4* nodes;
+  const float4* tris;
+  const float4* spheres;
+  const int2* sphere_meta;
+  const float4* mats;
+  const float* emitter_cdf;
+  const float4* emitters;
+  const float4* sky_pixels;
+  int n_nodes, n_tris, n_spheres, n_emitters;
+  float emission_area;
+  int sky_type;
+  float sky_color[3];
+  int sky_height;
+  float sky_longitude_offset;
+  LrCamera cam;
+};
+
+struct DevParams {
+  int integrator;
+  int spp_begin, spp_count;
+  int depth, depth_limit, no_direct_emitter;
+  unsigned long long seed;
+  int crop_x, crop_y, crop_w, crop_h;
+  int splits;
+  int tiles_x, tiles_y;                  // 8x4 pixel tiles over the crop window
+};
+
+// device counter block (unsigned long long each)
+enum CounterSlot { C_RAYS = 0, C_NONFINITE = 1, C_NODES = 2, C_TRIS = 3, C_SPHERES = 4, C_COUNT = 8 };
+
+}  // namespace lr

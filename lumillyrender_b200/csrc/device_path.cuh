@@ -39,6 +39,30 @@ LR_DEV float norm(F3 a) { return sqrtf(sqr_norm(a)); }
 LR_DEV F3 normalize(F3 a) { return a / norm(a); }            // three true divisions (traits.rs:38-42)
 LR_DEV float comp(F3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 
+// ------------------------------------------------------------------ sin/cos
+// The reference calls f32::sin / f32::cos, i.e. whatever the platform libm provides (not bit-defined).
+// The hot path needs them only for angles 2*pi*xi (BSDF / emitter / aperture sampling) and the
+// omnidirectional camera.  One fp32 algorithm is specified here and restated verbatim in the oracle
+// (oracle.cpp: spec_sincos) so that sampled directions — and therefore every later hit — replay bit
+// for bit on CPU and GPU: Cody-Waite reduction by pi/2 in three parts, then the Cephes sinf/cosf
+// minimax polynomials on [-pi/4, pi/4] (<= 2 ulp), all in unfused fp32 operations.
+LR_DEV void spec_sincos(float x, float* sn, float* cs) {
+  const float kf = rintf(x * 0.636619772367581343f);           // round-to-nearest-even of x * 2/pi
+  const int k = (int)kf;
+  float r = x - kf * 1.5703125f;
+  r = r - kf * 4.837512969970703125e-4f;
+  r = r - kf * 7.54978995489188216e-8f;
+  const float z = r * r;
+  const float s = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
+  const float c = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z - 0.5f * z + 1.0f;
+  switch (k & 3) {
+    case 0: *sn = s; *cs = c; break;
+    case 1: *sn = c; *cs = -s; break;
+    case 2: *sn = -s; *cs = -c; break;
+    default: *sn = -c; *cs = s; break;
+  }
+}
+
 // ------------------------------------------------------------------ RNG (replaces rand::random)
 // Counter-based: the stream of a sample is a pure function of (seed, pixel, sample index), so any
 // GPU can render any sample range and reproduce it bit for bit.  PCG32 (XSH-RR 64/32) stepped from
@@ -374,7 +398,7 @@ LR_DEV void mat_sample(const Mat& m, F3 out_, F3 n, Pcg& rng, F3& in_, float& pd
   const float xi2 = rng.next();
   const float r1 = 2.0f * kPI * xi1;
   float s1, c1;
-  sincosf(r1, &s1, &c1);
+  spec_sincos(r1, &s1, &c1);
   switch (m.type) {
     case LR_MAT_LAMBERT: {                                         // lambert.rs:37-55 + util.rs:87-96
       F3 u, v;
@@ -466,7 +490,7 @@ LR_DEV F3 cam_aperture_point(const LrCamera& c, float xi1, float xi2) {         
   const float u = 2.0f * kPI * xi1;
   const float v = sqrtf(xi2) * c.aperture_radius;
   float su, cu;
-  sincosf(u, &su, &cu);
+  spec_sincos(u, &su, &cu);
   return f3(c.aperture_position) + f3(c.right) * (cu * v) + f3(c.up) * (su * v);
 }
 LR_DEV float cam_geometry_term(const LrCamera& c, F3 direction) {                      // camera.rs:302-309
@@ -490,8 +514,8 @@ LR_DEV void camera_sample(const LrCamera& c, int x, int y, Draw&& draw, F3& o, F
     const float p = ((float)x + u) / (float)c.width * kPI * 2.0f;
     const float t = ((float)y + v) / (float)c.height * kPI;
     float sp, cp, st, ct;
-    sincosf(p, &sp, &cp);
-    sincosf(t, &st, &ct);
+    spec_sincos(p, &sp, &cp);
+    spec_sincos(t, &st, &ct);
     o = f3(c.aperture_position);
     d = f3(st * cp, st * sp, ct);
     g_term = 1.0f;

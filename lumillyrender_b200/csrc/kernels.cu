@@ -135,7 +135,7 @@ render_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ DevPa
                   const float r2 = u2 * 2.0f - 1.0f;
                   const float r2s = sqrtf(1.0f - r2 * r2);
                   float sn, cs;
-                  sincosf(r1, &sn, &cs);
+                  spec_sincos(r1, &sn, &cs);
                   q = f3(e0) + e1.x * f3(cs * r2s, sn * r2s, r2);
                 }
                 nee_pdf = (1.0f / area) * area / sc.emission_area;

@@ -65,6 +65,31 @@ inline float powi(float a, int b) {
   return recip ? 1.0f / r : r;
 }
 
+// ---------------------------------------------------------------- sin/cos
+// The reference calls f32::sin / f32::cos = the platform libm (not bit-defined across platforms).
+// math mode 0 uses libm like the reference; math mode 1 uses the fp32 algorithm specified for the device
+// (csrc/device_path.cuh: spec_sincos, restated here operation for operation) so that replay comparisons
+// are not perturbed by 1-ulp libm differences.  tests/ check that the two modes differ by <= 2 ulp.
+thread_local int g_math_mode = 0;
+inline void spec_sincos(float x, float* sn, float* cs) {
+  const float kf = std::nearbyint(x * 0.636619772367581343f);
+  const int k = (int)kf;
+  float r = x - kf * 1.5703125f;
+  r = r - kf * 4.837512969970703125e-4f;
+  r = r - kf * 7.54978995489188216e-8f;
+  const float z = r * r;
+  const float s = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
+  const float c = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z - 0.5f * z + 1.0f;
+  switch (k & 3) {
+    case 0: *sn = s; *cs = c; break;
+    case 1: *sn = c; *cs = -s; break;
+    case 2: *sn = -s; *cs = -c; break;
+    default: *sn = -c; *cs = s; break;
+  }
+}
+inline float osin(float x) { if (g_math_mode == 0) return std::sin(x); float s, c; spec_sincos(x, &s, &c); return s; }
+inline float ocos(float x) { if (g_math_mode == 0) return std::cos(x); float s, c; spec_sincos(x, &s, &c); return c; }
+
 // ---------------------------------------------------------------- RNG
 // The reference draws rand::random::<f32>() (rand 0.3: 24 random mantissa bits, [0,1)) from an
 // OS-seeded thread-local generator, so its renders are not reproducible and
@@ -168,13 +193,13 @@ inline V3 hemisphere_cos_importance(float xi1, float xi2) {              // util
   const float r1 = 2.0f * PI * xi1;
   const float r2 = xi2;
   const float r2s = std::sqrt(r2);
-  return v3(std::cos(r1) * r2s, std::sin(r1) * r2s, std::sqrt(1.0f - r2));
+  return v3(ocos(r1) * r2s, osin(r1) * r2s, std::sqrt(1.0f - r2));
 }
 inline V3 sphere_uniform(float xi1, float xi2) {                         // util.rs:108-116
   const float r1 = 2.0f * PI * xi1;
   const float r2 = xi2 * 2.0f - 1.0f;
   const float r2s = std::sqrt(1.0f - r2 * r2);
-  return v3(std::cos(r1) * r2s, std::sin(r1) * r2s, r2);
+  return v3(ocos(r1) * r2s, osin(r1) * r2s, r2);
 }
 
 // ---------------------------------------------------------------- materials (src/material/*.rs)
@@ -322,7 +347,7 @@ inline MatSample mat_sample(const LrMaterial& m, V3 out_, V3 n, Rng& rng) {
       const float r2 = rng.next();
       const float t = std::pow(r2, 1.0f / (a + 2.0f));
       const float ts = std::sqrt(1.0f - t * t);
-      const V3 in_ = u * std::cos(r1) * ts + v * std::sin(r1) * ts + w * t;
+      const V3 in_ = u * ocos(r1) * ts + v * osin(r1) * ts + w * t;
       const float c = dot(r, in_);
       return MatSample{in_, (a + 2.0f) / (2.0f * PI) * std::pow(c, a)};
     }
@@ -336,7 +361,7 @@ inline MatSample mat_sample(const LrMaterial& m, V3 out_, V3 n, Rng& rng) {
       const float r2 = rng.next();
       const float t = std::pow(r2, 1.0f / (a + 2.0f));
       const float ts = std::sqrt(1.0f - t * t);
-      const V3 h = u * std::cos(r1) * ts + v * std::sin(r1) * ts + w * t;
+      const V3 h = u * ocos(r1) * ts + v * osin(r1) * ts + w * t;
       const V3 in_ = h * (2.0f * dot(out_, h)) - out_;
       const float c = dot(on, h);
       return MatSample{in_, (a + 2.0f) / (2.0f * PI) * std::pow(c, a)};
@@ -352,7 +377,7 @@ inline MatSample mat_sample(const LrMaterial& m, V3 out_, V3 n, Rng& rng) {
       const float x = 1.0f + tan * tan;
       const float c = 1.0f / std::sqrt(x);
       const float s = tan / std::sqrt(x);
-      const V3 h = u * std::cos(r1) * s + v * std::sin(r1) * s + w * c;
+      const V3 h = u * ocos(r1) * s + v * osin(r1) * s + w * c;
       const float o_h = dot(out_, h);
       const V3 in_ = h * (2.0f * o_h) - out_;
       const float jacobian = 1.0f / (4.0f * o_h);
@@ -812,8 +837,8 @@ inline V3 cam_sample_sensor(const LrCamera& c, int left, int top, float u, float
 inline V3 cam_sample_aperture(const LrCamera& c, float xi1, float xi2) {                // camera.rs:285-300, 430-445
   const float u = 2.0f * PI * xi1;
   const float v = std::sqrt(xi2) * c.aperture_radius;
-  const float px = std::cos(u) * v;
-  const float py = std::sin(u) * v;
+  const float px = ocos(u) * v;
+  const float py = osin(u) * v;
   return from3(c.aperture_position) + from3(c.right) * px + from3(c.up) * py;
 }
 inline float cam_geometry_term(const LrCamera& c, V3 direction) {                       // camera.rs:302-309, 447-454
@@ -835,7 +860,7 @@ static CamSample camera_sample(const LrCamera& c, int x, int y, Draw draw) {
       const float u = draw(); const float v = draw();
       const float p = ((float)x + u) / (float)c.width * PI * 2.0f;
       const float t = ((float)y + v) / (float)c.height * PI;
-      const V3 direction = v3(std::sin(t) * std::cos(p), std::sin(t) * std::sin(p), std::cos(t));
+      const V3 direction = v3(osin(t) * ocos(p), osin(t) * osin(p), ocos(t));
       return CamSample{Ray{from3(c.aperture_position), direction}, 1.0f, 1.0f};
     }
     case LR_CAM_PINHOLE: {                                                              // camera.rs:313-328
@@ -955,7 +980,7 @@ void orc_scene_destroy(OrcScene* s) { delete s; }
 int orc_scene_nodes(const OrcScene* s) { return (int)s->impl.bvh.nodes.size(); }
 
 // main.rs:92-121 — one job per pixel, all samples of the pixel summed in order
-int orc_render(const OrcScene* s, const LrRenderParams* p, int traversal, int rng_mode, int n_threads,
+int orc_render(const OrcScene* s, const LrRenderParams* p, int traversal, int rng_mode, int math_mode, int n_threads,
                int pixel_stride, float* out_sum, float* out_sumsq, OrcStats* stats) {
   if (!s || !p || !out_sum) return LR_ERR_INVALID;
   const SceneImpl& sc = s->impl;
@@ -971,6 +996,7 @@ int orc_render(const OrcScene* s, const LrRenderParams* p, int traversal, int rn
   std::vector<uint64_t> nonfinite(n_threads, 0), nsamples(n_threads, 0);
   const auto t0 = std::chrono::steady_clock::now();
   auto worker = [&](int tid) {
+    g_math_mode = math_mode;
     Rng rng;
     Integrator in{sc, Tracer{sc, traversal, Counters{}}, rng, p->depth, p->depth_limit, p->no_direct_emitter != 0};
     const int64_t chunk = 64;
@@ -1033,6 +1059,7 @@ int orc_trace_primary(const OrcScene* s, float u, float v, float ua, float va, i
   if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
   std::atomic<int> next_row{0};
   auto worker = [&]() {
+    g_math_mode = 1;   // the probe is a GPU-parity tool: aperture sampling uses the specified sincos
     Tracer tr{sc, traversal, Counters{}};
     while (true) {
       const int y = next_row.fetch_add(1);
@@ -1068,6 +1095,9 @@ int orc_trace_rays(const OrcScene* s, int64_t n, const float* origins, const flo
   }
   return LR_OK;
 }
+
+void orc_set_math_mode(int mode) { g_math_mode = mode; }
+void orc_spec_sincos(float x, float* s, float* c) { spec_sincos(x, s, c); }
 
 int orc_camera_sample(const LrCamera* cam, int x, int y, float u, float v, float ua, float va, float* out9) {
   int k = 0;

@@ -40,8 +40,12 @@ int orc_scene_nodes(const OrcScene* s);
 /* out_sum: crop_w*crop_h*3 per-pixel SUM over the sample range (not the mean),
  * out_sumsq: nullable, per-pixel sum of squares.  Pixel jobs are distributed over n_threads
  * (0 = hardware_concurrency), each pixel runs all its samples in order (main.rs:92-104). */
-int orc_render(const OrcScene* s, const LrRenderParams* p, int traversal, int rng_mode,
+/* math_mode: 0 = libm sin/cos like the reference, 1 = the fp32 sincos specified for the device
+ *            (bit-identical sampled directions on CPU and GPU). */
+int orc_render(const OrcScene* s, const LrRenderParams* p, int traversal, int rng_mode, int math_mode,
                int n_threads, int pixel_stride, float* out_sum, float* out_sumsq, OrcStats* stats);
+void orc_set_math_mode(int mode);     /* for the calling thread (unit-level entry points) */
+void orc_spec_sincos(float x, float* s, float* c);
 
 int orc_trace_primary(const OrcScene* s, float u, float v, float ua, float va, int traversal,
                       int n_threads, int32_t* prim, float* t);

@@ -45,7 +45,9 @@ def lib():
         L.orc_scene_create.argtypes = [C.POINTER(LrSceneDesc), C.POINTER(C.c_void_p)]
         L.orc_scene_destroy.argtypes = [C.c_void_p]
         L.orc_scene_nodes.argtypes = [C.c_void_p]
-        L.orc_render.argtypes = [C.c_void_p, C.POINTER(LrRenderParams), C.c_int, C.c_int, C.c_int, C.c_int, _PF, _PF, C.POINTER(OrcStats)]
+        L.orc_render.argtypes = [C.c_void_p, C.POINTER(LrRenderParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _PF, _PF, C.POINTER(OrcStats)]
+        L.orc_set_math_mode.argtypes = [C.c_int]
+        L.orc_spec_sincos.argtypes = [C.c_float, _PF, _PF]
         L.orc_trace_primary.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _PI, _PF]
         L.orc_trace_rays.argtypes = [C.c_void_p, C.c_int64, _PF, _PF, C.c_int, C.c_int, _PI, _PF, _PF]
         L.orc_camera_sample.argtypes = [C.POINTER(LrCamera), C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _PF]
@@ -109,14 +111,15 @@ class OracleScene:
         cam = desc_ptr.contents.camera
         self.width, self.height = cam.width, cam.height
 
-    def render(self, params, traversal=0, rng_mode=0, threads=0, pixel_stride=1, sumsq=True):
-        """Returns (per-pixel SUM image, sumsq, stats).  traversal 0 = faithful reference algorithm."""
+    def render(self, params, traversal=0, rng_mode=0, math_mode=1, threads=0, pixel_stride=1, sumsq=True):
+        """Returns (per-pixel SUM image, sumsq, stats).  traversal 0 = faithful reference algorithm;
+        math_mode 1 = the specified fp32 sincos shared with the device, 0 = libm like the reference."""
         h = params.crop_h if params.crop_w > 0 else self.height
         w = params.crop_w if params.crop_w > 0 else self.width
         out = np.zeros((h, w, 3), dtype=np.float32)
         sq = np.zeros((h, w, 3), dtype=np.float32) if sumsq else None
         st = OrcStats()
-        rc = self._L.orc_render(self._s, C.byref(params), traversal, rng_mode, threads, pixel_stride, fp(out),
+        rc = self._L.orc_render(self._s, C.byref(params), traversal, rng_mode, math_mode, threads, pixel_stride, fp(out),
                                 fp(sq) if sumsq else None, C.byref(st))
         if rc != 0:
             raise RuntimeError("orc_render failed: %d" % rc)

@@ -2,8 +2,10 @@
 
 Bars (BASELINE.json north_star / SURVEY.md §8d):
   * primary-ray nearest hit: primitive index equal on >= 99.99 % of pixels, |t_gpu - t_ref| <= 1e-5 * t_ref;
-  * replay (shared counter-based RNG): per-pixel means agree within rtol 2e-3 on >= 97 % of pixels — the
-    residue is paths that diverged on a 1-ulp difference between CUDA's and glibc's sin/cos/pow;
+  * replay (shared counter-based RNG + the specified fp32 sincos): the path GEOMETRY replays bit for bit, so
+    the ray counts are equal and per-pixel means agree within rtol 1e-4 on >= 99.9 % of pixels (the residue
+    is fp32 rounding of the iterative throughput form vs the reference's recursion; Phong / Blinn-Phong also
+    call powf, where CUDA and glibc differ by an ulp and a path may diverge: rtol 1e-3 on >= 99.5 %);
   * statistical (independent RNG streams): per channel |mean_g - mean_r| <= 3 sigma on >= 99 % of channels and
     the image-mean difference within 4 standard errors; relMSE printed.
 """
@@ -115,15 +117,20 @@ def test_random_rays_match_brute_force_oracle(lr, orc, gpu, n_tris, n_spheres):
 def test_replay_matches_oracle(scenes, lr, name, spp):
     d, s, o = scenes(name)
     img, sq, st = s.render(spp=spp, seed=11, splits=1, sumsq=True)
-    ref_sum, ref_sq, ost = o.render(make_params(lr, d.config, spp=spp, seed=11), traversal=0, rng_mode=0)
+    ref_sum, ref_sq, ost = o.render(make_params(lr, d.config, spp=spp, seed=11), traversal=0, rng_mode=0, math_mode=1)
     ref = ref_sum / spp
     finite = np.isfinite(ref).all(-1) & np.isfinite(img).all(-1)
-    close = np.isclose(img, ref, rtol=2e-3, atol=2e-4).all(-1)
-    frac = close[finite].mean()
-    print("%s: replay agreement %.4f, rays gpu %d oracle %d" % (name, frac, st["rays"], ost["rays"]))
-    assert frac >= 0.97
-    assert abs(st["rays"] - ost["rays"]) <= 0.01 * ost["rays"]
-    assert st["nonfinite_samples"] <= ost["nonfinite_samples"] + 4
+    uses_powf = name in ("brdf-phong", "brdf-blinn")
+    rtol, need = (1e-3, 0.995) if uses_powf else (1e-4, 0.999)
+    frac = np.isclose(img, ref, rtol=rtol, atol=rtol * 0.1).all(-1)[finite].mean()
+    frac_sq = np.isclose(sq, ref_sq, rtol=10 * rtol, atol=rtol).all(-1)[finite].mean()
+    print("%s: replay agreement %.5f (sumsq %.5f) at rtol %g, rays gpu %d oracle %d" % (name, frac, frac_sq, rtol, st["rays"], ost["rays"]))
+    assert frac >= need and frac_sq >= need
+    if uses_powf:
+        assert abs(st["rays"] - ost["rays"]) <= 1e-3 * ost["rays"]
+    else:
+        assert st["rays"] == ost["rays"], "path geometry must replay exactly"
+    assert st["nonfinite_samples"] == ost["nonfinite_samples"] or uses_powf
 
 
 @pytest.mark.parametrize("name,spp", [("primitive", 32), ("new-cbox", 64), ("brdf", 32), ("brdf-phong", 32), ("brdf-blinn", 32),

@@ -22,6 +22,27 @@ def _iptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_int32))
 
 
+def params_from_config(cfg, integrator=None, spp=None, spp_begin=0, seed=0, crop=None, splits=0, count=False,
+                       depth=None, depth_limit=None, no_direct_emitter=None):
+    """LrRenderParams from the scene's [renderer] table with optional overrides."""
+    p = LrRenderParams()
+    if integrator is None:
+        p.integrator = cfg.integrator
+    else:
+        p.integrator = INTEGRATORS[integrator] if isinstance(integrator, str) else int(integrator)
+    p.spp_begin = int(spp_begin)
+    p.spp_count = int(spp if spp is not None else cfg.samples)
+    p.depth = int(cfg.depth if depth is None else depth)
+    p.depth_limit = int(cfg.depth_limit if depth_limit is None else depth_limit)
+    p.no_direct_emitter = int(cfg.no_direct_emitter if no_direct_emitter is None else no_direct_emitter)
+    p.seed = int(seed)
+    if crop:
+        p.crop_x, p.crop_y, p.crop_w, p.crop_h = [int(v) for v in crop]
+    p.splits = int(splits)
+    p.count_traversal = 1 if count else 0
+    return p
+
+
 class Description:
     """`Description::new(path)` — loads a scene TOML through the host front end (C++)."""
 
@@ -89,25 +110,8 @@ class Scene:
         check(self._lib.lr_scene_bytes(self._s, C.byref(b)))
         return b.value
 
-    def params(self, integrator=None, spp=None, spp_begin=0, seed=0, crop=None, splits=0, count=False,
-               depth=None, depth_limit=None, no_direct_emitter=None):
-        cfg = self.config
-        p = LrRenderParams()
-        if integrator is None:
-            p.integrator = cfg.integrator
-        else:
-            p.integrator = INTEGRATORS[integrator] if isinstance(integrator, str) else int(integrator)
-        p.spp_begin = int(spp_begin)
-        p.spp_count = int(spp if spp is not None else cfg.samples)
-        p.depth = int(cfg.depth if depth is None else depth)
-        p.depth_limit = int(cfg.depth_limit if depth_limit is None else depth_limit)
-        p.no_direct_emitter = int(cfg.no_direct_emitter if no_direct_emitter is None else no_direct_emitter)
-        p.seed = int(seed)
-        if crop:
-            p.crop_x, p.crop_y, p.crop_w, p.crop_h = [int(v) for v in crop]
-        p.splits = int(splits)
-        p.count_traversal = 1 if count else 0
-        return p
+    def params(self, **kw):
+        return params_from_config(self.config, **kw)
 
     def _shape(self, p):
         return (p.crop_h, p.crop_w, 3) if p.crop_w > 0 else (self.height, self.width, 3)

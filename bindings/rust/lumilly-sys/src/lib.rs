@@ -1,0 +1,58 @@
+//! UNTESTED SOURCE (no Rust toolchain offline).  `extern "C"` declarations of include/lumilly.h — the
+//! drop-in boundary that replaces the `pool.scoped(..)` + channel-gather block of the reference's
+//! `src/main.rs:70-132`.  Field order and types mirror the C structs one to one.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)] #[derive(Clone, Copy)] pub struct LrMaterial { pub type_: i32, pub color: [f32; 3], pub emission: [f32; 3], pub param0: f32, pub param1: f32 }
+#[repr(C)] #[derive(Clone, Copy)] pub struct LrTriangle { pub p0: [f32; 3], pub p1: [f32; 3], pub p2: [f32; 3], pub material: i32, pub prim_id: i32 }
+#[repr(C)] #[derive(Clone, Copy)] pub struct LrSphere { pub center: [f32; 3], pub radius: f32, pub material: i32, pub prim_id: i32 }
+#[repr(C)] #[derive(Clone, Copy)] pub struct LrCamera {
+    pub type_: i32, pub width: i32, pub height: i32,
+    pub forward: [f32; 3], pub right: [f32; 3], pub up: [f32; 3], pub position: [f32; 3], pub aperture_position: [f32; 3],
+    pub sensor_size: [f32; 2], pub aperture_radius: f32, pub aperture_sensor_distance: f32,
+    pub sensor_pixel_area: f32, pub sensor_sensitivity: f32, pub focus_distance: f32,
+}
+#[repr(C)] #[derive(Clone, Copy)] pub struct LrSky { pub type_: i32, pub color: [f32; 3], pub pixels: *const f32, pub n_pixels: i64, pub height: i32, pub longitude_offset: f32 }
+#[repr(C)] #[derive(Clone, Copy)] pub struct LrBvhNode { pub f: [f32; 12], pub c: [i32; 2], pub n: [i32; 2] }
+#[repr(C)] pub struct LrSceneDesc {
+    pub materials: *const LrMaterial, pub n_materials: i32,
+    pub triangles: *const LrTriangle, pub n_triangles: i32,
+    pub spheres: *const LrSphere, pub n_spheres: i32,
+    pub nodes: *const LrBvhNode, pub n_nodes: i32,
+    pub bvh_depth: i32, pub camera: LrCamera, pub sky: LrSky,
+}
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct LrRenderParams {
+    pub integrator: i32, pub spp_begin: i32, pub spp_count: i32, pub depth: i32, pub depth_limit: i32, pub no_direct_emitter: i32,
+    pub seed: u64, pub crop_x: i32, pub crop_y: i32, pub crop_w: i32, pub crop_h: i32, pub splits: i32, pub count_traversal: i32,
+}
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct LrStats {
+    pub rays: u64, pub samples: u64, pub nodes_visited: u64, pub tris_tested: u64, pub spheres_tested: u64, pub nonfinite_samples: u64,
+    pub kernel_ms: f32, pub launches: i32, pub splits: i32,
+}
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct LrSceneConfig {
+    pub samples: i32, pub depth: i32, pub depth_limit: i32, pub no_direct_emitter: i32, pub threads: i32, pub integrator: i32,
+    pub width: i32, pub height: i32, pub output: i32, pub gamma: f32, pub n_prims: i32, pub n_emitters: i32, pub bvh_build_seconds: f32,
+}
+pub enum LrScene {}
+pub enum LrHostScene {}
+
+extern "C" {
+    pub fn lr_abi_version() -> c_int;
+    pub fn lr_init(device: c_int) -> c_int;
+    pub fn lr_shutdown();
+    pub fn lr_last_error() -> *const c_char;
+    pub fn lr_scene_create(desc: *const LrSceneDesc, out: *mut *mut LrScene) -> c_int;
+    pub fn lr_scene_destroy(scene: *mut LrScene);
+    pub fn lr_render(scene: *const LrScene, params: *const LrRenderParams, out_rgb: *mut f32, out_sumsq: *mut f32, stats: *mut LrStats) -> c_int;
+    pub fn lr_render_accumulate_device(scene: *const LrScene, params: *const LrRenderParams, d_sum: *mut f32, d_sumsq: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn lr_stats_fetch(scene: *const LrScene, stream: *mut c_void, stats: *mut LrStats) -> c_int;
+    pub fn lr_trace_primary(scene: *const LrScene, u: f32, v: f32, ua: f32, va: f32, prim: *mut i32, t: *mut f32) -> c_int;
+    pub fn lr_host_scene_load(toml_path: *const c_char, asset_root: *const c_char, w: i32, h: i32, out: *mut *mut LrHostScene) -> c_int;
+    pub fn lr_host_scene_from_arrays(materials: *const LrMaterial, n_materials: i32, triangles: *const LrTriangle, n_triangles: i32,
+                                     spheres: *const LrSphere, n_spheres: i32, camera: *const LrCamera, sky: *const LrSky,
+                                     out: *mut *mut LrHostScene) -> c_int;
+    pub fn lr_host_scene_desc(hs: *const LrHostScene) -> *const LrSceneDesc;
+    pub fn lr_host_scene_config(hs: *const LrHostScene, cfg: *mut LrSceneConfig) -> c_int;
+    pub fn lr_host_scene_free(hs: *mut LrHostScene);
+}

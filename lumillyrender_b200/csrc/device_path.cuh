@@ -168,11 +168,15 @@ LR_DEV void trace(const DevScene& sc, F3 o, F3 d, float& t_out, int& id_out, Tra
   if (sc.n_nodes > 0) {
     // conservative cull distance: a primitive's computed t may precede its box's computed entry
     float cull_t = best_t < 3.0e38f ? best_t * 1.0001f + 1e-4f : 3.0e38f;
+    // "while-while" traversal: every lane first descends inner nodes until it holds a leaf (or is done),
+    // the warp reconverges, then the lanes that hold leaves test triangles together.
+    constexpr int kDone = (int)0x80000000;       // not a valid leaf code (first triangle would be 2^28 - 1)
     int stack[kStackDepth];
     int sp = 0;
+    stack[sp++] = kDone;
     int cur = 0;
-    while (true) {
-      if (cur >= 0) {
+    while (cur != kDone) {
+      while (cur >= 0) {
         const float4* np = sc.nodes + 4 * (size_t)cur;
         const float4 n0 = ldg4(np + 0), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
         if (COUNT) tc.nodes++;
@@ -193,11 +197,15 @@ LR_DEV void trace(const DevScene& sc, F3 o, F3 d, float& t_out, int& id_out, Tra
           const bool first0 = en0 <= en1;
           stack[sp++] = first0 ? c1 : c0;
           cur = first0 ? c0 : c1;
-          continue;
+        } else if (h0) {
+          cur = c0;
+        } else if (h1) {
+          cur = c1;
+        } else {
+          cur = stack[--sp];
         }
-        if (h0) { cur = c0; continue; }
-        if (h1) { cur = c1; continue; }
-      } else {
+      }
+      if (cur != kDone) {
         const int code = ~cur;
         const int first = code >> 3;
         const int count = (code & 7) + 1;
@@ -218,9 +226,8 @@ LR_DEV void trace(const DevScene& sc, F3 o, F3 d, float& t_out, int& id_out, Tra
             }
           }
         }
+        cur = stack[--sp];
       }
-      if (sp == 0) break;
-      cur = stack[--sp];
     }
   }
   t_out = best_t;

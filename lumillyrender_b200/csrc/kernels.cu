@@ -48,34 +48,40 @@ render_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ DevPa
   TraceCounters tc;
   tc.nodes = tc.tris = tc.spheres = 0;
 
-  if (active) {
-    const int x = p.crop_x + lx, y = p.crop_y + ly;
-    const unsigned int pixel = (unsigned int)(y * sc.cam.width + x);
-    // sample sub-range of this split
-    const int per = p.spp_count / p.splits, rem = p.spp_count % p.splits;
-    int s = p.spp_begin + split * per + min(split, rem);
-    const int s_end = s + per + (split < rem ? 1 : 0);
+  // Warp-synchronous loop: every iteration all lanes of the warp meet at __any_sync, lanes with work
+  // trace ONE ray together (extension or shadow), then shade.  Lanes whose pixel is finished stay in the
+  // loop (idle) until the whole warp is done, so the reconvergence points are well defined.
+  const unsigned kFull = 0xffffffffu;
+  const int x = p.crop_x + lx, y = p.crop_y + ly;
+  const unsigned int pixel = (unsigned int)(y * sc.cam.width + x);
+  // sample sub-range of this split
+  const int per = p.spp_count / p.splits, rem = p.spp_count % p.splits;
+  int s = p.spp_begin + split * per + min(split, rem);
+  const int s_end = active ? s + per + (split < rem ? 1 : 0) : s;
 
-    F3 sum = f3(0.0f, 0.0f, 0.0f), sumsq = f3(0.0f, 0.0f, 0.0f);
-    Pcg rng;
-    rng.state = 0;
-    // path state
-    F3 o = f3(0, 0, 0), d = f3(0, 0, 1);
-    F3 T = f3(1, 1, 1), L = f3(0, 0, 0);
-    float cam_g = 1.0f, cam_w = 1.0f;
-    int depth = 0;
-    bool allow_emission = true;
-    bool need_new = true;
-    // vertex state (kept across the NEE shadow ray)
-    bool shadow = false;
-    F3 v_pos = f3(0, 0, 0), v_n = f3(0, 0, 1), v_wo = f3(0, 0, 1);
-    int v_mat = 0;
-    float v_prr = 1.0f, v_dist = 0.0f;
-    float nee_dist = 0.0f, nee_sqr = 1.0f, nee_pdf = 1.0f;
+  F3 sum = f3(0.0f, 0.0f, 0.0f), sumsq = f3(0.0f, 0.0f, 0.0f);
+  Pcg rng;
+  rng.state = 0;
+  // path state
+  F3 o = f3(0, 0, 0), d = f3(0, 0, 1);
+  F3 T = f3(1, 1, 1), L = f3(0, 0, 0);
+  float cam_g = 1.0f, cam_w = 1.0f;
+  int depth = 0;
+  bool allow_emission = true;
+  bool need_new = true;
+  bool live = active;
+  // vertex state (kept across the NEE shadow ray)
+  bool shadow = false;
+  F3 v_pos = f3(0, 0, 0), v_n = f3(0, 0, 1), v_wo = f3(0, 0, 1);
+  int v_mat = 0;
+  float v_prr = 1.0f, v_dist = 0.0f;
+  float nee_dist = 0.0f, nee_sqr = 1.0f, nee_pdf = 1.0f;
 
-    while (true) {
-      if (need_new) {
-        if (s >= s_end) break;
+  while (true) {
+    if (live && need_new) {
+      if (s >= s_end) {
+        live = false;
+      } else {
         rng.seed(p.seed, pixel, (unsigned int)s);
         camera_sample(sc.cam, x, y, [&]() { return rng.next(); }, o, d, cam_g, cam_w);
         T = f3(1.0f, 1.0f, 1.0f);
@@ -85,13 +91,20 @@ render_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ DevPa
         need_new = false;
         shadow = false;
       }
+    }
+    if (!__any_sync(kFull, live)) break;
 
-      float t;
-      int id;
+    float t = 0.0f;
+    int id = -1;
+    if (live) {
       trace<COUNT>(sc, o, d, t, id, tc);          // Objects::intersect (objects.rs:63-65)
       n_rays++;
+    }
+    __syncwarp(kFull);
 
+    if (live) {
       bool finish = false;
+      bool sample_bsdf = false;
       if (!shadow) {
         if (id == -1) {
           L = L + T * sky_radiance(sc, d);        // scene.rs:29 / 43
@@ -111,6 +124,7 @@ render_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ DevPa
             finish = true;
           } else {
             v_pos = sf.pos; v_n = sf.n; v_wo = wo; v_mat = sf.mat; v_prr = prr; v_dist = t;
+            sample_bsdf = true;
             if (INTEGRATOR == LR_INTEGRATOR_PT_DIRECT) {
               allow_emission = false;             // every deeper vertex: no_emission = true (scene.rs:189)
               // direct_light_radiance: scene.rs:104-125
@@ -147,8 +161,8 @@ render_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ DevPa
                   nee_sqr = sqr_norm(direct_path);
                   o = sf.pos;
                   d = dir;
-                  shadow = true;
-                  continue;                       // trace the shadow ray at the common call site
+                  shadow = true;                  // the shadow ray is traced at the common call site next iteration
+                  sample_bsdf = false;
                 }
               }
             }
@@ -157,6 +171,7 @@ render_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ DevPa
       } else {
         // visibility + contribution: scene.rs:127-150
         shadow = false;
+        sample_bsdf = true;
         if (id != -1 && fabsf(t - nee_dist) <= kEPS) {
           const Surface lf = surface_at(sc, o, d, t, id);
           const float light_cos = dot(-d, lf.n);
@@ -174,7 +189,7 @@ render_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ DevPa
         }
       }
 
-      if (!finish) {
+      if (sample_bsdf) {
         // material_interaction_radiance: scene.rs:78-102
         const Mat m = load_mat(sc, v_mat);
         F3 wi;
@@ -187,18 +202,21 @@ render_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ DevPa
         o = v_pos;                                // no origin offset (scene.rs:94-97)
         d = wi;
         depth++;
-        continue;
       }
 
-      // main.rs:99-102
-      const F3 e = (L * cam_g) * cam_w;
-      if (!(isfinite(e.x) && isfinite(e.y) && isfinite(e.z))) n_nonfinite++;
-      sum = sum + e;
-      if (SUMSQ) sumsq = sumsq + e * e;
-      s++;
-      need_new = true;
+      if (finish) {
+        // main.rs:99-102
+        const F3 e = (L * cam_g) * cam_w;
+        if (!(isfinite(e.x) && isfinite(e.y) && isfinite(e.z))) n_nonfinite++;
+        sum = sum + e;
+        if (SUMSQ) sumsq = sumsq + e * e;
+        s++;
+        need_new = true;
+      }
     }
+  }
 
+  if (active) {
     const size_t pi = (size_t)ly * p.crop_w + lx;
     const size_t n_px = (size_t)p.crop_w * p.crop_h;
     if (p.splits == 1) {

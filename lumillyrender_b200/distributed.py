@@ -33,5 +33,8 @@ def render_sharded(accumulate, accum, spp_total, rank, world, dist=None, dst=0):
         dist.reduce(accum, dst=dst, op=dist.ReduceOp.SUM)
     if rank != dst:
         return None
-    accum /= float(spp_total)          # `estimated_sum / spp as f32` (main.rs:104), after the cross-GPU sum
+    # `estimated_sum / spp as f32` (main.rs:104) after the cross-GPU sum.  A tensor divisor keeps it a true
+    # division (torch turns division by a Python scalar into a multiplication by the reciprocal on CUDA).
+    import torch
+    accum.div_(torch.full((), float(spp_total), dtype=accum.dtype, device=accum.device))
     return accum

@@ -193,7 +193,7 @@ def test_accumulate_device_matches_render(scenes, lr):
     s.render_accumulate(acc.data_ptr(), acc_sq.data_ptr(), stream=stream, spp=6, seed=4, splits=1)
     st = s.stats(stream)
     assert st["samples"] == s.width * s.height * 6 and st["rays"] > 0
-    assert np.array_equal((acc / 6.0).cpu().numpy(), ref)
+    assert np.array_equal(acc.cpu().numpy() / np.float32(6.0), ref)
     assert np.array_equal(acc_sq.cpu().numpy(), ref_sq)
 
 

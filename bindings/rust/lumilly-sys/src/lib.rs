@@ -20,7 +20,7 @@ use std::os::raw::{c_char, c_int, c_void};
     pub triangles: *const LrTriangle, pub n_triangles: i32,
     pub spheres: *const LrSphere, pub n_spheres: i32,
     pub nodes: *const LrBvhNode, pub n_nodes: i32,
-    pub bvh_depth: i32, pub camera: LrCamera, pub sky: LrSky,
+    pub bvh_depth: i32, pub n_flat_triangles: i32, pub camera: LrCamera, pub sky: LrSky,
 }
 #[repr(C)] #[derive(Clone, Copy, Default)] pub struct LrRenderParams {
     pub integrator: i32, pub spp_begin: i32, pub spp_count: i32, pub depth: i32, pub depth_limit: i32, pub no_direct_emitter: i32,
@@ -28,7 +28,7 @@ use std::os::raw::{c_char, c_int, c_void};
 }
 #[repr(C)] #[derive(Clone, Copy, Default)] pub struct LrStats {
     pub rays: u64, pub samples: u64, pub nodes_visited: u64, pub tris_tested: u64, pub spheres_tested: u64, pub nonfinite_samples: u64,
-    pub kernel_ms: f32, pub launches: i32, pub splits: i32,
+    pub gate_retraces: u64, pub kernel_ms: f32, pub launches: i32, pub splits: i32,
 }
 #[repr(C)] #[derive(Clone, Copy, Default)] pub struct LrSceneConfig {
     pub samples: i32, pub depth: i32, pub depth_limit: i32, pub no_direct_emitter: i32, pub threads: i32, pub integrator: i32,

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LR_ABI_VERSION 1
+#define LR_ABI_VERSION 2
 
 typedef enum LrStatus {
   LR_OK = 0,
@@ -115,8 +115,8 @@ typedef struct LrSky {
  *   f[0..5]  = child0 lo.xyz, hi.xyz      f[6..11] = child1 lo.xyz, hi.xyz
  *   c[0],c[1]= child index: >= 0 inner node; < 0 leaf, first triangle = ~c
  *   n[0],n[1]= triangle count of a leaf child (0 for inner, <0 for "no child")
- * Leaves reference contiguous ranges of LrSceneDesc.triangles (already permuted
- * into leaf order by lr_bvh_build).                                              */
+ * Leaves reference contiguous ranges of the first n_triangles - n_flat_triangles entries of
+ * LrSceneDesc.triangles (already permuted into leaf order by the host front end).             */
 typedef struct LrBvhNode {
   float f[12];
   int32_t c[2];
@@ -127,8 +127,11 @@ typedef struct LrSceneDesc {
   const LrMaterial* materials; int32_t n_materials;
   const LrTriangle* triangles; int32_t n_triangles;   /* in BVH leaf order      */
   const LrSphere* spheres;     int32_t n_spheres;
-  const LrBvhNode* nodes;      int32_t n_nodes;       /* 0 nodes iff 0 triangles */
+  const LrBvhNode* nodes;      int32_t n_nodes;       /* 0 nodes iff no triangle is in the BVH */
   int32_t bvh_depth;                                    /* max stack depth needed */
+  int32_t n_flat_triangles;    /* the LAST n_flat_triangles entries of `triangles` are outside the BVH: large
+                                  primitives (walls, floors, area lights) that every ray tests in a flat loop,
+                                  like the spheres.  0 <= n_flat_triangles <= n_triangles.                   */
   LrCamera camera;
   LrSky sky;
 } LrSceneDesc;
@@ -160,6 +163,8 @@ typedef struct LrStats {
   uint64_t tris_tested;
   uint64_t spheres_tested;
   uint64_t nonfinite_samples;  /* samples whose estimate was NaN/Inf (kept, as the reference does) */
+  uint64_t gate_retraces;      /* rays re-traced strictly because their optimistic nearest BVH hit failed the
+                                  reference's leaf-AABB gate (a few per 10^8 rays)                  */
   float kernel_ms;             /* CUDA-event time of the render kernel(s)        */
   int32_t launches;            /* kernels launched by the call                    */
   int32_t splits;              /* splits actually used                            */

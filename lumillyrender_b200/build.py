@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblumilly_b200.so")
 CLI = os.path.join(HERE, "bin", "lumilly")
 SOURCES = ["kernels.cu", "api.cpp", "bvh_build.cpp", "toml_obj.cpp", "host_scene.cpp", "image_io.cpp"]
-HEADERS = ["device_scene.h", "device_path.cuh", "kernels.h", "common.h", "host_scene.h", "../../include/lumilly.h"]
+HEADERS = ["device_scene.h", "device_path.cuh", "persistent.cuh", "kernels.h", "common.h", "host_scene.h", "../../include/lumilly.h"]
 
 
 def _nvcc():
@@ -35,20 +35,39 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build_library(force=False, verbose=False):
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    if not force and not _stale(LIB, deps):
-        return LIB
-    cmd = [
-        _nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
-        "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
-        "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-fvisibility=default",
-        "-shared", "-o", LIB,
-    ] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lz"]
+def _compile(job):
+    cmd, verbose = job
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True)
+
+
+def build_library(force=False, verbose=False):
+    """Compiles every translation unit to build/*.o in parallel (the render kernel is instantiated in two
+    units, one per integrator, see csrc/persistent_inst.cu) and links liblumilly_b200.so."""
+    from concurrent.futures import ThreadPoolExecutor
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS + ["persistent_inst.cu"]] + [os.path.abspath(__file__)]
+    if not force and not _stale(LIB, deps):
+        return LIB
+    obj_dir = os.path.join(HERE, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
+             "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
+             "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-fvisibility=default"]
+    if verbose:
+        flags.insert(0, "-Xptxas=-v")
+    jobs, objs = [], []
+    for src in SOURCES:
+        o = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
+        objs.append(o)
+        jobs.append(([_nvcc()] + flags + ["-c", os.path.join(CSRC, src), "-o", o], verbose))
+    for integ in (0, 1):
+        o = os.path.join(obj_dir, "persistent_i%d.o" % integ)
+        objs.append(o)
+        jobs.append(([_nvcc()] + flags + ["-DLR_INST_INTEGRATOR=%d" % integ, "-c", os.path.join(CSRC, "persistent_inst.cu"), "-o", o], verbose))
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        list(ex.map(_compile, jobs))
+    subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lz"], check=True)
     return LIB
 
 

@@ -49,7 +49,7 @@ class LrBvhNode(C.Structure):
 class LrSceneDesc(C.Structure):
     _fields_ = [("materials", C.POINTER(LrMaterial)), ("n_materials", i32), ("triangles", C.POINTER(LrTriangle)), ("n_triangles", i32),
                 ("spheres", C.POINTER(LrSphere)), ("n_spheres", i32), ("nodes", C.POINTER(LrBvhNode)), ("n_nodes", i32),
-                ("bvh_depth", i32), ("camera", LrCamera), ("sky", LrSky)]
+                ("bvh_depth", i32), ("n_flat_triangles", i32), ("camera", LrCamera), ("sky", LrSky)]
 
 
 class LrRenderParams(C.Structure):
@@ -60,7 +60,7 @@ class LrRenderParams(C.Structure):
 
 class LrStats(C.Structure):
     _fields_ = [("rays", u64), ("samples", u64), ("nodes_visited", u64), ("tris_tested", u64), ("spheres_tested", u64),
-                ("nonfinite_samples", u64), ("kernel_ms", f32), ("launches", i32), ("splits", i32)]
+                ("nonfinite_samples", u64), ("gate_retraces", u64), ("kernel_ms", f32), ("launches", i32), ("splits", i32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

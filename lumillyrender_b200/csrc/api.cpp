@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -201,6 +202,11 @@ int lr_scene_create(const LrSceneDesc* d, LrScene** out) {
     return fail(LR_ERR_CUDA, msg);
   }
   dv.n_nodes = d->n_nodes; dv.n_tris = d->n_triangles; dv.n_spheres = d->n_spheres; dv.n_emitters = (int)ems.size();
+  dv.n_bvh_tris = d->n_triangles - d->n_flat_triangles;
+  for (int k = 0; k < 3; k++) {
+    dv.bvh_lo[k] = d->n_nodes > 0 ? std::fmin(d->nodes[0].f[k], d->nodes[0].f[6 + k]) : 0.0f;
+    dv.bvh_hi[k] = d->n_nodes > 0 ? std::fmax(d->nodes[0].f[3 + k], d->nodes[0].f[9 + k]) : 0.0f;
+  }
   dv.emission_area = area;
   dv.sky_type = d->sky.type;
   dv.sky_color[0] = d->sky.color[0]; dv.sky_color[1] = d->sky.color[1]; dv.sky_color[2] = d->sky.color[2];
@@ -248,6 +254,7 @@ static int resolve_params(const LrScene* s, const LrRenderParams* p, DevParams& 
   }
   dp.tiles_x = (dp.crop_w + 7) / 8; dp.tiles_y = (dp.crop_h + 3) / 4;
   int splits = p->splits;
+  if (const char* e_splits = std::getenv("LR_SPLITS")) splits = std::atoi(e_splits);   // development knob
   if (splits <= 0) {
     // auto: enough threads for ~2 full waves of 148 SMs x 2048 resident threads, >= 4 samples per thread
     const long long px_threads = (long long)dp.tiles_x * dp.tiles_y * 32;
@@ -259,6 +266,12 @@ static int resolve_params(const LrScene* s, const LrRenderParams* p, DevParams& 
   const size_t px = (size_t)dp.crop_w * dp.crop_h;
   while (splits > 1 && px * 3 * sizeof(float) * splits > (1ull << 30)) splits--;
   dp.splits = splits;
+  // kernel organisation knobs (development / profiling only; defaults are the measured best)
+  const char* e_di = std::getenv("LR_DEFER_ITERS");
+  const char* e_dt = std::getenv("LR_DEFER_THRESH");
+  dp.defer_iters = e_di ? std::max(1, std::atoi(e_di)) : 4;
+  dp.defer_thresh = e_dt ? std::max(1, std::min(32, std::atoi(e_dt))) : 16;
+
   return LR_OK;
 }
 
@@ -293,8 +306,14 @@ int lr_render_accumulate_device(const LrScene* s, const LrRenderParams* p, float
     s->ev_pending = false;
   }
   LR_CUDA(cudaEventRecord(s->ev0, st));
-  LR_CUDA(launch_render(s->dev, dp, p->count_traversal != 0, d_sumsq != nullptr, ksum, ksq, s->d_counters, st));
-  s->acc_launches++;
+  {
+    // the unit cursor lives in the last word of the counter block (reset on the stream before every launch)
+    unsigned int* next_unit = reinterpret_cast<unsigned int*>(s->d_counters + C_NEXT_UNIT);
+    LR_CUDA(cudaMemsetAsync(next_unit, 0, sizeof(unsigned long long), st));
+    LR_CUDA(launch_render_persistent(s->dev, dp, p->count_traversal != 0, ksum, d_sumsq ? ksq : nullptr, s->d_counters, next_unit,
+                                     std::max(g_sm_count, 1), st));
+    s->acc_launches++;
+  }
   if (dp.splits > 1) {
     LR_CUDA(launch_reduce_splits(d_sum, s->d_partial, n, dp.splits, st));
     s->acc_launches++;
@@ -322,7 +341,7 @@ int lr_stats_fetch(const LrScene* s, void* cuda_stream, LrStats* stats) {
   LR_CUDA(cudaMemcpy(c, s->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
   LR_CUDA(cudaMemset(s->d_counters, 0, sizeof(c)));
   std::memset(stats, 0, sizeof(*stats));
-  stats->rays = c[C_RAYS]; stats->nonfinite_samples = c[C_NONFINITE];
+  stats->rays = c[C_RAYS]; stats->nonfinite_samples = c[C_NONFINITE]; stats->gate_retraces = c[C_RETRACE];
   stats->nodes_visited = c[C_NODES]; stats->tris_tested = c[C_TRIS]; stats->spheres_tested = c[C_SPHERES];
   stats->samples = s->acc_samples; stats->kernel_ms = s->acc_kernel_ms; stats->launches = s->acc_launches; stats->splits = s->last_splits;
   s->acc_samples = 0; s->acc_kernel_ms = 0.0f; s->acc_launches = 0;

@@ -6,6 +6,12 @@
 // same cost model T_aabb = 1, T_tri = 2 as bvh.rs:71-72), leaves of up to 4 triangles (8 at most),
 // child boxes stored in the parent and padded outward so the device's node test is conservative,
 // nodes emitted in depth-first order (a node's near child is usually the next node in memory).
+//
+// Large triangles stay OUTSIDE the tree ("flat list", tested by every ray like the spheres): a wall or floor
+// whose box spans the scene is reached by every ray anyway, and in a tree it only forces all rays through a
+// few near-root leaves in ray-dependent order — divergent work on a GPU — while a fixed flat loop runs in
+// lock-step.  With the walls out, the tree bounds only the meshes, so most rays of a path tracer in a room
+// never enter it.  The nearest hit is the minimum over all candidates either way.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -34,6 +40,9 @@ constexpr int kBins = 16;
 constexpr int kLeafTarget = 4;     // stop splitting at <= 4 triangles
 constexpr int kLeafMax = 8;        // leaf code holds count-1 in 3 bits
 constexpr int kSahDepthLimit = 32; // deeper than this: median splits only, so depth <= 32 + log2(n) < 64
+constexpr int kFlatAllBelow = 16;  // scenes with this many triangles or fewer: no tree at all
+constexpr int kFlatMax = 24;       // at most this many large triangles are kept outside the tree
+constexpr float kFlatAreaFraction = 0.01f;
 
 struct Builder {
   const std::vector<Box>& tri_box;
@@ -142,14 +151,52 @@ struct Builder {
 
 }  // namespace
 
-int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, int& depth_out, float& seconds_out) {
+int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, int& depth_out, float& seconds_out, int& n_flat_out) {
   const auto t0 = std::chrono::steady_clock::now();
   nodes_out.clear();
   depth_out = 0;
   seconds_out = 0.0f;
-  const int n = (int)tris.size();
-  if (n == 0) return LR_OK;
-  if (n >= (1 << 28)) return fail(LR_ERR_UNSUPPORTED, "more than 2^28 triangles");
+  n_flat_out = 0;
+  const int n_all = (int)tris.size();
+  if (n_all == 0) return LR_OK;
+  if (n_all >= (1 << 28)) return fail(LR_ERR_UNSUPPORTED, "more than 2^28 triangles");
+  // ---- flat list selection: all triangles of a tiny scene, else the (at most kFlatMax) largest triangles whose
+  // box area is >= kFlatAreaFraction of the scene's box area
+  Box scene; scene.reset();
+  {
+    std::vector<float> area(n_all);
+    for (int i = 0; i < n_all; i++) {
+      Box b; b.reset();
+      b.grow(tris[i].p0); b.grow(tris[i].p1); b.grow(tris[i].p2);
+      for (int k = 0; k < 3; k++)
+        if (!std::isfinite(b.lo[k]) || !std::isfinite(b.hi[k])) return fail(LR_ERR_INVALID, "non-finite triangle vertex");
+      area[i] = b.area();
+      scene.grow(b);
+    }
+    std::vector<int> flat;
+    if (n_all <= kFlatAllBelow) {
+      for (int i = 0; i < n_all; i++) flat.push_back(i);
+    } else {
+      const float thresh = kFlatAreaFraction * scene.area();
+      for (int i = 0; i < n_all; i++) if (area[i] >= thresh && area[i] > 0.0f) flat.push_back(i);
+      if ((int)flat.size() > kFlatMax) {
+        std::stable_sort(flat.begin(), flat.end(), [&](int a, int b) { return area[a] > area[b]; });
+        flat.resize(kFlatMax);
+        std::sort(flat.begin(), flat.end());
+      }
+    }
+    if (!flat.empty()) {
+      std::vector<char> is_flat(n_all, 0);
+      for (int i : flat) is_flat[i] = 1;
+      std::vector<LrTriangle> re; re.reserve(n_all);
+      for (int i = 0; i < n_all; i++) if (!is_flat[i]) re.push_back(tris[i]);
+      for (int i : flat) re.push_back(tris[i]);            // instance order is kept inside the flat list
+      tris.swap(re);
+      n_flat_out = (int)flat.size();
+    }
+  }
+  const int n = n_all - n_flat_out;                        // triangles that go into the tree: tris[0, n)
+  if (n == 0) { seconds_out = std::chrono::duration<float>(std::chrono::steady_clock::now() - t0).count(); return LR_OK; }
   std::vector<Box> tri_box(n);
   std::vector<Vec3> centroid(n);
   std::vector<int> order(n);
@@ -166,7 +213,7 @@ int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, 
   }
   Builder bld{tri_box, centroid, order, {}, 0, 0.0f};
   float extent = 0.0f;
-  for (int k = 0; k < 3; k++) extent = std::fmax(extent, std::fmax(std::fabs(all.lo[k]), std::fabs(all.hi[k])));
+  for (int k = 0; k < 3; k++) extent = std::fmax(extent, std::fmax(std::fabs(scene.lo[k]), std::fabs(scene.hi[k])));   // whole scene: ray origins lie on any surface
   bld.pad = 4e-6f * extent + 1e-30f;     // > the rounding error of (box - origin) * inv, see device_path.cuh
   bld.nodes.reserve((size_t)n / 2 + 16);
   if (n == 1) {
@@ -179,7 +226,7 @@ int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, 
   } else {
     bld.build_inner(0, n, all, 0);
   }
-  std::vector<LrTriangle> permuted(n);
+  std::vector<LrTriangle> permuted(tris);                  // the flat tail stays where it is
   for (int i = 0; i < n; i++) permuted[i] = tris[order[i]];
   tris.swap(permuted);
   nodes_out.swap(bld.nodes);
@@ -193,7 +240,9 @@ int validate_desc(const LrSceneDesc& d) {
   if (d.n_materials < 0 || d.n_triangles < 0 || d.n_spheres < 0 || d.n_nodes < 0) return fail(LR_ERR_INVALID, "negative count");
   if ((d.n_materials > 0 && !d.materials) || (d.n_triangles > 0 && !d.triangles) || (d.n_spheres > 0 && !d.spheres) || (d.n_nodes > 0 && !d.nodes))
     return fail(LR_ERR_INVALID, "null array with non-zero count");
-  if ((d.n_triangles > 0) != (d.n_nodes > 0)) return fail(LR_ERR_INVALID, "BVH nodes must be present iff triangles are present (use lr_bvh_build / lr_host_scene_from_arrays)");
+  if (d.n_flat_triangles < 0 || d.n_flat_triangles > d.n_triangles) return fail(LR_ERR_INVALID, "n_flat_triangles out of range");
+  const int n_bvh_tris = d.n_triangles - d.n_flat_triangles;
+  if ((n_bvh_tris > 0) != (d.n_nodes > 0)) return fail(LR_ERR_INVALID, "BVH nodes must be present iff triangles are in the BVH (use lr_host_scene_from_arrays)");
   if (d.bvh_depth >= 64) return fail(LR_ERR_UNSUPPORTED, "BVH deeper than the device traversal stack (64)");
   const int n_prims = d.n_triangles + d.n_spheres;
   for (int i = 0; i < d.n_materials; i++)
@@ -214,7 +263,7 @@ int validate_desc(const LrSceneDesc& d) {
       if (c >= 0) { if (c >= d.n_nodes) return fail(LR_ERR_INVALID, "BVH child index out of range"); }
       else {
         const int code = ~c, first = code >> 3, count = (code & 7) + 1;
-        if (first < 0 || first + count > d.n_triangles) return fail(LR_ERR_INVALID, "BVH leaf range out of bounds");
+        if (first < 0 || first + count > n_bvh_tris) return fail(LR_ERR_INVALID, "BVH leaf range out of bounds");
       }
     }
   }

@@ -145,15 +145,12 @@ struct TraceCounters { unsigned int nodes, tris, spheres; };
 
 LR_DEV float4 ldg4(const float4* p) { return __ldg(p); }
 
-// Nearest hit.  id: -1 miss, >= 0 triangle index (leaf order), <= -2 sphere index = -2 - id.
-// Spheres are tested first by a flat loop (exact reference arithmetic, no culling at all: the
-// r = 1e5 ground sphere of scenes/primitive.toml has a t error far larger than any box slack).
+// Candidates every ray tests in a fixed order, with the reference's exact arithmetic and its leaf-AABB gate:
+// the spheres (no culling at all: the r = 1e5 ground sphere of scenes/primitive.toml has a t error far larger
+// than any box slack), then the flat list of large triangles tris[n_bvh_tris, n_tris) (bvh_build.cpp).
+// id: -1 miss, >= 0 triangle index, <= -2 sphere index = -2 - id.
 template <bool COUNT>
-LR_DEV void trace(const DevScene& sc, F3 o, F3 d, float& t_out, int& id_out, TraceCounters& tc) {
-  const F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-  float best_t = 3.0e38f;
-  int best = -1;
-
+LR_DEV void flat_hits(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, int& best, TraceCounters& tc) {
   for (int i = 0; i < sc.n_spheres; i++) {
     const float4 s = ldg4(sc.spheres + i);
     if (COUNT) tc.spheres++;
@@ -164,72 +161,126 @@ LR_DEV void trace(const DevScene& sc, F3 o, F3 d, float& t_out, int& id_out, Tra
       if (ref_slab_pass(c - r, c + r, o, inv)) { best_t = t; best = -2 - i; }
     }
   }
+  for (int i = sc.n_bvh_tris; i < sc.n_tris; i++) {
+    const float4* tp = sc.tris + 3 * (size_t)i;
+    const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
+    if (COUNT) tc.tris++;
+    const F3 p0 = f3(v0), p1 = f3(v1), p2 = f3(v2);
+    const float t = triangle_mt(p0, p1, p2, o, d);
+    if (t >= 0.0f && t < best_t) {
+      const F3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
+      const F3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
+      if (ref_slab_pass(lo, hi, o, inv)) { best_t = t; best = i; }
+    }
+  }
+}
 
-  if (sc.n_nodes > 0) {
-    // conservative cull distance: a primitive's computed t may precede its box's computed entry
-    float cull_t = best_t < 3.0e38f ? best_t * 1.0001f + 1e-4f : 3.0e38f;
-    // "while-while" traversal: every lane first descends inner nodes until it holds a leaf (or is done),
-    // the warp reconverges, then the lanes that hold leaves test triangles together.
-    constexpr int kDone = (int)0x80000000;       // not a valid leaf code (first triangle would be 2^28 - 1)
-    int stack[kStackDepth];
-    int sp = 0;
-    stack[sp++] = kDone;
-    int cur = 0;
-    while (cur != kDone) {
-      while (cur >= 0) {
-        const float4* np = sc.nodes + 4 * (size_t)cur;
-        const float4 n0 = ldg4(np + 0), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
-        if (COUNT) tc.nodes++;
-        // child 0: lo = (n0.x,n0.y,n0.z) hi = (n0.w,n1.x,n1.y); child 1: lo = (n1.z,n1.w,n2.x) hi = (n2.y,n2.z,n2.w)
-        const float ax0 = (n0.x - o.x) * inv.x, bx0 = (n0.w - o.x) * inv.x;
-        const float ay0 = (n0.y - o.y) * inv.y, by0 = (n1.x - o.y) * inv.y;
-        const float az0 = (n0.z - o.z) * inv.z, bz0 = (n1.y - o.z) * inv.z;
-        const float ax1 = (n1.z - o.x) * inv.x, bx1 = (n2.y - o.x) * inv.x;
-        const float ay1 = (n1.w - o.y) * inv.y, by1 = (n2.z - o.y) * inv.y;
-        const float az1 = (n2.x - o.z) * inv.z, bz1 = (n2.w - o.z) * inv.z;
-        const float en0 = fmaxf(fmaxf(fminf(ax0, bx0), fminf(ay0, by0)), fmaxf(fminf(az0, bz0), 0.0f));
-        const float ex0 = fminf(fminf(fmaxf(ax0, bx0), fmaxf(ay0, by0)), fminf(fmaxf(az0, bz0), cull_t));
-        const float en1 = fmaxf(fmaxf(fminf(ax1, bx1), fminf(ay1, by1)), fmaxf(fminf(az1, bz1), 0.0f));
-        const float ex1 = fminf(fminf(fmaxf(ax1, bx1), fmaxf(ay1, by1)), fminf(fmaxf(az1, bz1), cull_t));
-        const bool h0 = en0 <= ex0, h1 = en1 <= ex1;
-        const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-        if (h0 && h1) {
-          const bool first0 = en0 <= en1;
-          stack[sp++] = first0 ? c1 : c0;
-          cur = first0 ? c0 : c1;
-        } else if (h0) {
-          cur = c0;
-        } else if (h1) {
-          cur = c1;
-        } else {
-          cur = stack[--sp];
-        }
-      }
-      if (cur != kDone) {
-        const int code = ~cur;
-        const int first = code >> 3;
-        const int count = (code & 7) + 1;
-        for (int k = 0; k < count; k++) {
-          const float4* tp = sc.tris + 3 * (size_t)(first + k);
-          const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
-          if (COUNT) tc.tris++;
-          const F3 p0 = f3(v0), p1 = f3(v1), p2 = f3(v2);
-          const float t = triangle_mt(p0, p1, p2, o, d);
-          if (t >= 0.0f && t < best_t) {
-            // the leaf's own AABB gate (triangle.rs:102-119 box, aabb.rs:75-92 test)
-            const F3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
-            const F3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
-            if (ref_slab_pass(lo, hi, o, inv)) {
-              best_t = t;
-              best = first + k;
-              cull_t = best_t * 1.0001f + 1e-4f;
-            }
-          }
-        }
+// conservative: can the ray reach the tree's bounds within [0, cull_t]?  (same padded-box form as the node test)
+LR_DEV bool bvh_bounds_hit(const DevScene& sc, F3 o, F3 inv, float cull_t) {
+  const float ax = (sc.bvh_lo[0] - o.x) * inv.x, bx = (sc.bvh_hi[0] - o.x) * inv.x;
+  const float ay = (sc.bvh_lo[1] - o.y) * inv.y, by = (sc.bvh_hi[1] - o.y) * inv.y;
+  const float az = (sc.bvh_lo[2] - o.z) * inv.z, bz = (sc.bvh_hi[2] - o.z) * inv.z;
+  const float en = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+  const float ex = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), cull_t));
+  return en <= ex;
+}
+
+// BVH part of the nearest-hit query: "while-while" traversal (every lane first descends inner nodes until it holds
+// a leaf or is done, the warp reconverges, then the lanes that hold leaves test triangles together), near child
+// first, per-thread stack, nodes culled against [0, cull_t] on host-padded boxes.  best_t / best come in holding the
+// nearest flat candidate (or 3e38 / -1) and are replaced only by something strictly nearer.
+//   STRICT = true : a candidate must also pass the reference's gate on the triangle's own AABB (bvh.rs:21-25)
+//                   when it becomes the nearest — the reference's semantics, candidate by candidate.
+//   STRICT = false: optimistic accept; the caller gates the final nearest hit once (bvh_hit_is_gated) and falls back
+//                   to the strict query if it fails.  If the nearest candidate passes, it IS the gated nearest hit
+//                   (the minimum over a superset that lies in the subset).
+template <bool COUNT, bool STRICT>
+LR_DEV void bvh_traverse(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, int& best, TraceCounters& tc) {
+  // conservative cull distance: a primitive's computed t may precede its box's computed entry
+  float cull_t = best_t < 3.0e38f ? best_t * 1.0001f + 1e-4f : 3.0e38f;
+  constexpr int kDone = (int)0x80000000;       // not a valid leaf code (first triangle would be 2^28 - 1)
+  int stack[kStackDepth];
+  int sp = 0;
+  stack[sp++] = kDone;
+  int cur = 0;
+  while (cur != kDone) {
+    while (cur >= 0) {
+      const float4* np = sc.nodes + 4 * (size_t)cur;
+      const float4 n0 = ldg4(np + 0), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
+      if (COUNT) tc.nodes++;
+      // child 0: lo = (n0.x,n0.y,n0.z) hi = (n0.w,n1.x,n1.y); child 1: lo = (n1.z,n1.w,n2.x) hi = (n2.y,n2.z,n2.w)
+      const float ax0 = (n0.x - o.x) * inv.x, bx0 = (n0.w - o.x) * inv.x;
+      const float ay0 = (n0.y - o.y) * inv.y, by0 = (n1.x - o.y) * inv.y;
+      const float az0 = (n0.z - o.z) * inv.z, bz0 = (n1.y - o.z) * inv.z;
+      const float ax1 = (n1.z - o.x) * inv.x, bx1 = (n2.y - o.x) * inv.x;
+      const float ay1 = (n1.w - o.y) * inv.y, by1 = (n2.z - o.y) * inv.y;
+      const float az1 = (n2.x - o.z) * inv.z, bz1 = (n2.w - o.z) * inv.z;
+      const float en0 = fmaxf(fmaxf(fminf(ax0, bx0), fminf(ay0, by0)), fmaxf(fminf(az0, bz0), 0.0f));
+      const float ex0 = fminf(fminf(fmaxf(ax0, bx0), fmaxf(ay0, by0)), fminf(fmaxf(az0, bz0), cull_t));
+      const float en1 = fmaxf(fmaxf(fminf(ax1, bx1), fminf(ay1, by1)), fmaxf(fminf(az1, bz1), 0.0f));
+      const float ex1 = fminf(fminf(fmaxf(ax1, bx1), fmaxf(ay1, by1)), fminf(fmaxf(az1, bz1), cull_t));
+      const bool h0 = en0 <= ex0, h1 = en1 <= ex1;
+      const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+      if (h0 && h1) {
+        const bool first0 = en0 <= en1;
+        stack[sp++] = first0 ? c1 : c0;
+        cur = first0 ? c0 : c1;
+      } else if (h0) {
+        cur = c0;
+      } else if (h1) {
+        cur = c1;
+      } else {
         cur = stack[--sp];
       }
     }
+    if (cur != kDone) {
+      const int code = ~cur;
+      const int first = code >> 3;
+      const int count = (code & 7) + 1;
+      for (int k = 0; k < count; k++) {
+        const float4* tp = sc.tris + 3 * (size_t)(first + k);
+        const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
+        if (COUNT) tc.tris++;
+        const F3 p0 = f3(v0), p1 = f3(v1), p2 = f3(v2);
+        const float t = triangle_mt(p0, p1, p2, o, d);
+        if (t >= 0.0f && t < best_t) {
+          bool ok = true;
+          if (STRICT) {
+            // the leaf's own AABB gate (triangle.rs:102-119 box, aabb.rs:75-92 test)
+            const F3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
+            const F3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
+            ok = ref_slab_pass(lo, hi, o, inv);
+          }
+          if (ok) {
+            best_t = t;
+            best = first + k;
+            cull_t = best_t * 1.0001f + 1e-4f;
+          }
+        }
+      }
+      cur = stack[--sp];
+    }
   }
+}
+
+// the reference's gate (aabb.rs:75-92 on the triangle's own box, as Leaf::may_intersect applies it) for one BVH hit
+LR_DEV bool bvh_hit_is_gated(const DevScene& sc, F3 o, F3 inv, int id) {
+  const float4* tp = sc.tris + 3 * (size_t)id;
+  const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
+  const F3 p0 = f3(v0), p1 = f3(v1), p2 = f3(v2);
+  const F3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
+  const F3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
+  return ref_slab_pass(lo, hi, o, inv);
+}
+
+// Nearest hit: flat candidates first, then the BVH (strict `<`, so on exact ties the earlier candidate stays).
+template <bool COUNT>
+LR_DEV void trace(const DevScene& sc, F3 o, F3 d, float& t_out, int& id_out, TraceCounters& tc) {
+  const F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+  float best_t = 3.0e38f;
+  int best = -1;
+  flat_hits<COUNT>(sc, o, d, inv, best_t, best, tc);
+  if (sc.n_nodes > 0) bvh_traverse<COUNT, true>(sc, o, d, inv, best_t, best, tc);
   t_out = best_t;
   id_out = best;
 }
@@ -336,54 +387,52 @@ LR_DEV float fresnel_exact(float n1, float n2, F3 out_, F3 in_, F3 on) {        
 
 // Material::brdf
 LR_DEV F3 mat_brdf(const Mat& m, F3 out_, F3 in_, F3 n, F3 pos) {
-  switch (m.type) {
-    case LR_MAT_LAMBERT: {                                         // lambert.rs:32-35
-      const float c = checker(pos.x, pos.z);
-      return m.color * f3(c, c, c) / kPI;
+  if (m.type == LR_MAT_LAMBERT) {                                  // lambert.rs:32-35
+    const float c = checker(pos.x, pos.z);
+    return m.color * f3(c, c, c) / kPI;
+  }
+  if (m.type == LR_MAT_GGX) {                                      // ggx.rs:71-85
+    const F3 on = orienting_normal(out_, n);
+    if (dot(in_, on) <= 0.0f) return f3(0.0f, 0.0f, 0.0f);
+    const F3 h = normalize(in_ + out_);
+    const float alpha = m.param0 * m.param0;
+    const float a2 = alpha * alpha;
+    const float nnn = 1.0f - m.param1, nnp = 1.0f + m.param1;     // ggx.rs:41-47
+    const float f_0 = (nnn * nnn) / (nnp * nnp);
+    const float f = f_0 + (1.0f - f_0) * powi5(1.0f - dot(in_, h));
+    const float g = ggx_g1(a2, in_, on) * ggx_g1(a2, out_, on);
+    const float d = ggx_ndf(a2, h, on);
+    return m.color * f * g * d / (4.0f * dot(in_, on) * dot(out_, on));
+  }
+  if (m.type == LR_MAT_PHONG) {                                    // phong.rs:39-47
+    const F3 on = orienting_normal(out_, n);
+    if (dot(in_, on) <= 0.0f) return f3(0.0f, 0.0f, 0.0f);
+    const F3 r = reflect(out_, on);
+    const float c = dot(r, in_);
+    const float a = m.param0;
+    return m.color * ((a + 2.0f) / (2.0f * kPI) * powf(c, a));
+  }
+  if (m.type == LR_MAT_BLINN_PHONG) {                              // blinn_phong.rs:39-49
+    const F3 on = orienting_normal(out_, n);
+    if (dot(in_, on) <= 0.0f) return f3(0.0f, 0.0f, 0.0f);
+    const F3 h = normalize(in_ + out_);
+    const float c = dot(h, on);
+    const float a = m.param0;
+    return m.color * ((a + 2.0f) * (a + 4.0f) / (8.0f * kPI * (powf(2.0f, -a / 2.0f) + a)) * powf(c, a));
+  }
+  {                                                                // ideal_refraction.rs:40-68
+    const F3 on = orienting_normal(out_, n);
+    float from_ior, to_ior;
+    ior_pair(m, out_, n, from_ior, to_ior);
+    F3 r;
+    if (refract(out_, on, from_ior / to_ior, r)) {
+      const float fr = fresnel_exact(from_ior, to_ior, out_, r, on);
+      if (dot(in_, on) > 0.0f) return m.color * 1.0f / dot(in_, n) * fr;
+      const float q = to_ior / from_ior;
+      const float ft = (1.0f - fr) * (q * q);
+      return m.color * 1.0f / dot(in_, n) * ft;
     }
-    case LR_MAT_PHONG: {                                           // phong.rs:39-47
-      const F3 on = orienting_normal(out_, n);
-      if (dot(in_, on) <= 0.0f) return f3(0.0f, 0.0f, 0.0f);
-      const F3 r = reflect(out_, on);
-      const float c = dot(r, in_);
-      const float a = m.param0;
-      return m.color * ((a + 2.0f) / (2.0f * kPI) * powf(c, a));
-    }
-    case LR_MAT_BLINN_PHONG: {                                     // blinn_phong.rs:39-49
-      const F3 on = orienting_normal(out_, n);
-      if (dot(in_, on) <= 0.0f) return f3(0.0f, 0.0f, 0.0f);
-      const F3 h = normalize(in_ + out_);
-      const float c = dot(h, on);
-      const float a = m.param0;
-      return m.color * ((a + 2.0f) * (a + 4.0f) / (8.0f * kPI * (powf(2.0f, -a / 2.0f) + a)) * powf(c, a));
-    }
-    case LR_MAT_GGX: {                                             // ggx.rs:71-85
-      const F3 on = orienting_normal(out_, n);
-      if (dot(in_, on) <= 0.0f) return f3(0.0f, 0.0f, 0.0f);
-      const F3 h = normalize(in_ + out_);
-      const float alpha = m.param0 * m.param0;
-      const float a2 = alpha * alpha;
-      const float nnn = 1.0f - m.param1, nnp = 1.0f + m.param1;   // ggx.rs:41-47
-      const float f_0 = (nnn * nnn) / (nnp * nnp);
-      const float f = f_0 + (1.0f - f_0) * powi5(1.0f - dot(in_, h));
-      const float g = ggx_g1(a2, in_, on) * ggx_g1(a2, out_, on);
-      const float d = ggx_ndf(a2, h, on);
-      return m.color * f * g * d / (4.0f * dot(in_, on) * dot(out_, on));
-    }
-    default: {                                                     // ideal_refraction.rs:40-68
-      const F3 on = orienting_normal(out_, n);
-      float from_ior, to_ior;
-      ior_pair(m, out_, n, from_ior, to_ior);
-      F3 r;
-      if (refract(out_, on, from_ior / to_ior, r)) {
-        const float fr = fresnel_exact(from_ior, to_ior, out_, r, on);
-        if (dot(in_, on) > 0.0f) return m.color * 1.0f / dot(in_, n) * fr;
-        const float q = to_ior / from_ior;
-        const float ft = (1.0f - fr) * (q * q);
-        return m.color * 1.0f / dot(in_, n) * ft;
-      }
-      return m.color * 1.0f / dot(in_, n);
-    }
+    return m.color * 1.0f / dot(in_, n);
   }
 }
 
@@ -406,54 +455,52 @@ LR_DEV void mat_sample(const Mat& m, F3 out_, F3 n, Pcg& rng, F3& in_, float& pd
   const float r1 = 2.0f * kPI * xi1;
   float s1, c1;
   spec_sincos(r1, &s1, &c1);
-  switch (m.type) {
-    case LR_MAT_LAMBERT: {                                         // lambert.rs:37-55 + util.rs:87-96
-      F3 u, v;
-      orthonormal_basis(on, u, v);
-      const float r2s = sqrtf(xi2);
-      const F3 s = f3(c1 * r2s, s1 * r2s, sqrtf(1.0f - xi2));
-      in_ = u * s.x + v * s.y + on * s.z;
-      pdf = dot(in_, n) / kPI;
-      return;
-    }
-    case LR_MAT_PHONG: {                                           // phong.rs:49-69
-      const float a = m.param0;
-      const F3 r = reflect(out_, on);
-      F3 u, v;
-      orthonormal_basis(r, u, v);
-      const float t = powf(xi2, 1.0f / (a + 2.0f));
-      const float ts = sqrtf(1.0f - t * t);
-      in_ = u * c1 * ts + v * s1 * ts + r * t;
-      pdf = (a + 2.0f) / (2.0f * kPI) * powf(dot(r, in_), a);
-      return;
-    }
-    case LR_MAT_BLINN_PHONG: {                                     // blinn_phong.rs:51-73
-      const float a = m.param0;
-      F3 u, v;
-      orthonormal_basis(on, u, v);
-      const float t = powf(xi2, 1.0f / (a + 2.0f));
-      const float ts = sqrtf(1.0f - t * t);
-      const F3 h = u * c1 * ts + v * s1 * ts + on * t;
-      in_ = h * (2.0f * dot(out_, h)) - out_;
-      pdf = (a + 2.0f) / (2.0f * kPI) * powf(dot(on, h), a);
-      return;
-    }
-    default: {                                                     // ggx.rs:87-113
-      F3 u, v;
-      orthonormal_basis(on, u, v);
-      const float alpha = m.param0 * m.param0;
-      const float a2 = alpha * alpha;
-      const float tan = alpha * sqrtf(xi2 / (1.0f - xi2));
-      const float x = 1.0f + tan * tan;
-      const float c = 1.0f / sqrtf(x);
-      const float s = tan / sqrtf(x);
-      const F3 h = u * c1 * s + v * s1 * s + on * c;
-      const float o_h = dot(out_, h);
-      in_ = h * (2.0f * o_h) - out_;
-      const float jacobian = 1.0f / (4.0f * o_h);
-      pdf = ggx_ndf(a2, h, on) * dot(h, on) * jacobian;
-      return;
-    }
+  if (m.type == LR_MAT_LAMBERT) {                                  // lambert.rs:37-55 + util.rs:87-96
+    F3 u, v;
+    orthonormal_basis(on, u, v);
+    const float r2s = sqrtf(xi2);
+    const F3 s = f3(c1 * r2s, s1 * r2s, sqrtf(1.0f - xi2));
+    in_ = u * s.x + v * s.y + on * s.z;
+    pdf = dot(in_, n) / kPI;
+    return;
+  }
+  if (m.type == LR_MAT_GGX) {                                      // ggx.rs:87-113
+    F3 u, v;
+    orthonormal_basis(on, u, v);
+    const float alpha = m.param0 * m.param0;
+    const float a2 = alpha * alpha;
+    const float tan = alpha * sqrtf(xi2 / (1.0f - xi2));
+    const float x = 1.0f + tan * tan;
+    const float c = 1.0f / sqrtf(x);
+    const float s = tan / sqrtf(x);
+    const F3 h = u * c1 * s + v * s1 * s + on * c;
+    const float o_h = dot(out_, h);
+    in_ = h * (2.0f * o_h) - out_;
+    const float jacobian = 1.0f / (4.0f * o_h);
+    pdf = ggx_ndf(a2, h, on) * dot(h, on) * jacobian;
+    return;
+  }
+  if (m.type == LR_MAT_PHONG) {                                    // phong.rs:49-69
+    const float a = m.param0;
+    const F3 r = reflect(out_, on);
+    F3 u, v;
+    orthonormal_basis(r, u, v);
+    const float t = powf(xi2, 1.0f / (a + 2.0f));
+    const float ts = sqrtf(1.0f - t * t);
+    in_ = u * c1 * ts + v * s1 * ts + r * t;
+    pdf = (a + 2.0f) / (2.0f * kPI) * powf(dot(r, in_), a);
+    return;
+  }
+  {                                                                // blinn_phong.rs:51-73
+    const float a = m.param0;
+    F3 u, v;
+    orthonormal_basis(on, u, v);
+    const float t = powf(xi2, 1.0f / (a + 2.0f));
+    const float ts = sqrtf(1.0f - t * t);
+    const F3 h = u * c1 * ts + v * s1 * ts + on * t;
+    in_ = h * (2.0f * dot(out_, h)) - out_;
+    pdf = (a + 2.0f) / (2.0f * kPI) * powf(dot(on, h), a);
+    return;
   }
 }
 

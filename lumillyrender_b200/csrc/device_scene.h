@@ -3,7 +3,8 @@
 // Everything the kernels read is a flat, 16-byte aligned array so that every fetch on the
 // traversal path is a 128-bit load:
 //   nodes    : 4 x float4 per BVH node   (64 B)   — two child boxes + child codes
-//   tris     : 3 x float4 per triangle   (48 B)   — p0|prim_id, p1|material, p2|0   (BVH leaf order)
+//   tris     : 3 x float4 per triangle   (48 B)   — p0|prim_id, p1|material, p2|0   (BVH leaf order, then
+//                                                   the flat list of large triangles every ray tests)
 //   spheres  : 1 x float4 per sphere     (16 B)   — centre|radius     (+ int2 material/prim_id)
 //   mats     : 3 x float4 per material   (48 B)   — colour|type, emission|param0, param1|weight|emissive|0
 //   emitters : 3 x float4 per emitter    (48 B)   — tri: p0|kind, p1|area, p2|0 ; sphere: centre|kind, radius,0,0|area
@@ -28,6 +29,8 @@ struct DevScene {
   const float4* emitters;
   const float4* sky_pixels;
   int n_nodes, n_tris, n_spheres, n_emitters;
+  int n_bvh_tris;                        // tris[0, n_bvh_tris) are in BVH leaf order; tris[n_bvh_tris, n_tris) is the flat list
+  float bvh_lo[3], bvh_hi[3];            // bounds of the tree (union of the root's child boxes, padded like them)
   float emission_area;
   int sky_type;
   float sky_color[3];
@@ -44,9 +47,10 @@ struct DevParams {
   int crop_x, crop_y, crop_w, crop_h;
   int splits;
   int tiles_x, tiles_y;                  // 8x4 pixel tiles over the crop window
+  int defer_iters, defer_thresh;         // path vertices per phase A; suspended lanes that end it early (persistent.cuh)
 };
 
 // device counter block (unsigned long long each)
-enum CounterSlot { C_RAYS = 0, C_NONFINITE = 1, C_NODES = 2, C_TRIS = 3, C_SPHERES = 4, C_COUNT = 8 };
+enum CounterSlot { C_RAYS = 0, C_NONFINITE = 1, C_NODES = 2, C_TRIS = 3, C_SPHERES = 4, C_RETRACE = 5, C_NEXT_UNIT = 7, C_COUNT = 8 };
 
 }  // namespace lr

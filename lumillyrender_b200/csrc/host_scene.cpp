@@ -366,7 +366,9 @@ using namespace lr;
 int LrHostScene::finalize() {
   float seconds = 0.0f;
   int depth = 0;
-  if (int rc = build_bvh(triangles, nodes, depth, seconds)) return rc;
+  int n_flat = 0;
+  if (int rc = build_bvh(triangles, nodes, depth, seconds, n_flat)) return rc;
+  desc.n_flat_triangles = n_flat;
   desc.materials = materials.data(); desc.n_materials = (int)materials.size();
   desc.triangles = triangles.data(); desc.n_triangles = (int)triangles.size();
   desc.spheres = spheres.data(); desc.n_spheres = (int)spheres.size();

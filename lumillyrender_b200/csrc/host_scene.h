@@ -54,7 +54,8 @@ void camera_thin_lens(const Mat4& m, float xfov, float focus_distance, float f_n
 void camera_omnidirectional(const Mat4& m, int w, int h, LrCamera& out);
 void camera_pinhole(Vec3 position, Vec3 aperture_position, const float* sensor_size, int w, int h, float aperture_radius, LrCamera& out);
 
-int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, int& depth_out, float& seconds_out);
+// permutes `tris`: BVH leaf order first, then the `n_flat_out` large triangles kept outside the BVH
+int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, int& depth_out, float& seconds_out, int& n_flat_out);
 
 int load_hdr_file(const std::string& path, std::vector<float>& rgb, int& w, int& h);
 

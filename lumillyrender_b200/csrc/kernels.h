@@ -3,12 +3,18 @@
 #include "device_scene.h"
 
 namespace lr {
-cudaError_t launch_render(const DevScene& sc, const DevParams& p, bool count, bool sumsq, float* out_sum, float* out_sumsq,
-                          unsigned long long* counters, cudaStream_t stream);
+// the render kernel (persistent.cuh).  *next_unit must be 0 on `stream` before the launch.
+cudaError_t launch_render_persistent(const DevScene& sc, const DevParams& p, bool count, float* out_sum, float* out_sumsq,
+                                     unsigned long long* counters, unsigned int* next_unit, int sm_count, cudaStream_t stream);
+cudaError_t launch_persistent_i0(const DevScene& sc, const DevParams& p, bool count, float* out_sum, float* out_sumsq,
+                                 unsigned long long* counters, unsigned int* next_unit, int sm_count, cudaStream_t stream);
+cudaError_t launch_persistent_i1(const DevScene& sc, const DevParams& p, bool count, float* out_sum, float* out_sumsq,
+                                 unsigned long long* counters, unsigned int* next_unit, int sm_count, cudaStream_t stream);
 cudaError_t launch_reduce_splits(float* dst, const float* partial, size_t n, int splits, cudaStream_t stream);
 cudaError_t launch_scale(float* dst, size_t n, float divisor, cudaStream_t stream);
 cudaError_t launch_primary(const DevScene& sc, float u, float v, float ua, float va, int* prim, float* t, cudaStream_t stream);
 cudaError_t launch_rays(const DevScene& sc, long long n, const float* org, const float* dir, int* prim, float* t, float* nout,
                         cudaStream_t stream);
+
 cudaError_t launch_read_bw(const float4* buf, size_t n4, int iters, int blocks, float* sink, cudaStream_t stream);
 }  // namespace lr

@@ -31,8 +31,10 @@ def test_all_scenes_load(lr, assets, name):
     assert desc.n_triangles + desc.n_spheres == cfg.n_prims
     ids = sorted([desc.triangles[i].prim_id for i in range(desc.n_triangles)] + [desc.spheres[i].prim_id for i in range(desc.n_spheres)])
     assert ids == list(range(cfg.n_prims)), "primitive ids enumerate Loader.instances"
-    assert (desc.n_nodes > 0) == (desc.n_triangles > 0) and desc.bvh_depth < 64
-    # every triangle is referenced by exactly one leaf
+    n_bvh = desc.n_triangles - desc.n_flat_triangles
+    assert 0 <= desc.n_flat_triangles <= min(desc.n_triangles, 24)
+    assert (desc.n_nodes > 0) == (n_bvh > 0) and desc.bvh_depth < 64
+    # every triangle of the tree part is referenced by exactly one leaf; the flat tail (large triangles) by none
     seen = np.zeros(desc.n_triangles, dtype=np.int32)
     for i in range(desc.n_nodes):
         for k in range(2):
@@ -41,8 +43,9 @@ def test_all_scenes_load(lr, assets, name):
                 code = ~c
                 first, count = code >> 3, (code & 7) + 1
                 seen[first:first + count] += 1
-    if desc.n_triangles > 1:
-        assert (seen == 1).all()
+    if n_bvh > 1:
+        assert (seen[:n_bvh] == 1).all()
+    assert (seen[n_bvh:] == 0).all()
 
 
 def test_scene_config_values(lr, assets):

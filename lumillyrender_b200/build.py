@@ -42,18 +42,32 @@ def _compile(job):
     subprocess.run(cmd, check=True)
 
 
-def build_library(force=False, verbose=False):
+def build_variant(name, defines):
+    """Development: builds variants/lib_<name>.so with extra -D flags (A/B experiments, tools/ab.py)."""
+    global LIB
+    out = os.path.join(HERE, "variants", "lib_%s.so" % name)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    keep = LIB
+    try:
+        LIB = out
+        build_library(force=True, extra=["-D" + d for d in defines], obj_dir=os.path.join(HERE, "build", "variant_" + name))
+    finally:
+        LIB = keep
+    return out
+
+
+def build_library(force=False, verbose=False, extra=(), obj_dir=None):
     """Compiles every translation unit to build/*.o in parallel (the render kernel is instantiated in two
     units, one per integrator, see csrc/persistent_inst.cu) and links liblumilly_b200.so."""
     from concurrent.futures import ThreadPoolExecutor
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS + ["persistent_inst.cu"]] + [os.path.abspath(__file__)]
     if not force and not _stale(LIB, deps):
         return LIB
-    obj_dir = os.path.join(HERE, "build")
+    obj_dir = obj_dir or os.path.join(HERE, "build")
     os.makedirs(obj_dir, exist_ok=True)
     flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
              "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
-             "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-fvisibility=default"]
+             "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-fvisibility=default"] + list(extra)
     if verbose:
         flags.insert(0, "-Xptxas=-v")
     jobs, objs = [], []

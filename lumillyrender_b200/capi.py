@@ -135,8 +135,13 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if not os.path.exists(path) or os.environ.get("LUMILLY_REBUILD"):
+    path = os.environ.get("LUMILLY_LIB")            # development: A/B a variant build (tools/ab.py)
+    if path:
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+    else:
+        path = _build.LIB
+    if path == _build.LIB and (not os.path.exists(path) or os.environ.get("LUMILLY_REBUILD")):
         _build.build_library(force=bool(os.environ.get("LUMILLY_REBUILD")))
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():

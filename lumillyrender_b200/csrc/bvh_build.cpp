@@ -3,7 +3,7 @@
 // Replaces BVH::new / BVH::construct (src/bvh.rs:57-127).  The reference's full-sweep SAH with one
 // primitive per leaf is O(n log^2 n) and produces 2N-1 boxed nodes; the nearest hit does not depend
 // on the topology (device_path.cuh), so this build is free to differ: binned SAH (16 bins x 3 axes,
-// same cost model T_aabb = 1, T_tri = 2 as bvh.rs:71-72), leaves of up to 4 triangles (8 at most),
+// same cost model T_aabb = 1, T_tri = 2 as bvh.rs:71-72), leaves of up to 2 triangles (8 at most),
 // child boxes stored in the parent and padded outward so the device's node test is conservative,
 // nodes emitted in depth-first order (a node's near child is usually the next node in memory).
 //
@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -37,7 +38,8 @@ struct Box {
 };
 
 constexpr int kBins = 16;
-constexpr int kLeafTarget = 4;     // stop splitting at <= 4 triangles
+static int kLeafTarget = 2;        // stop splitting at <= 2 triangles (measured best of 1..8, profiles/r01_c_ab_s17.txt;
+                                   // LR_LEAF_TARGET: development knob)
 constexpr int kLeafMax = 8;        // leaf code holds count-1 in 3 bits
 constexpr int kSahDepthLimit = 32; // deeper than this: median splits only, so depth <= 32 + log2(n) < 64
 constexpr int kFlatAllBelow = 16;  // scenes with this many triangles or fewer: no tree at all
@@ -153,6 +155,7 @@ struct Builder {
 
 int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, int& depth_out, float& seconds_out, int& n_flat_out) {
   const auto t0 = std::chrono::steady_clock::now();
+  if (const char* e = std::getenv("LR_LEAF_TARGET")) kLeafTarget = std::max(1, std::min(8, std::atoi(e)));
   nodes_out.clear();
   depth_out = 0;
   seconds_out = 0.0f;

@@ -145,6 +145,24 @@ struct TraceCounters { unsigned int nodes, tris, spheres; };
 
 LR_DEV float4 ldg4(const float4* p) { return __ldg(p); }
 
+// the reference's gate (aabb.rs:75-92 on the triangle's own box, as Leaf::may_intersect applies it, bvh.rs:21-25)
+LR_DEV bool tri_gate(const DevScene& sc, F3 o, F3 inv, int id) {
+  const float4* tp = sc.tris + 3 * (size_t)id;
+  const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
+  const F3 p0 = f3(v0), p1 = f3(v1), p2 = f3(v2);
+  const F3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
+  const F3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
+  return ref_slab_pass(lo, hi, o, inv);
+}
+// flat triangle list with the gate on every candidate (the rare fallback of flat_hits), out of line
+static __device__ __noinline__ void flat_tris_strict(const DevScene& sc, F3 o, F3 d, F3 inv, float* best_t, int* best) {
+  for (int i = sc.n_bvh_tris; i < sc.n_tris; i++) {
+    const float4* tp = sc.tris + 3 * (size_t)i;
+    const float t = triangle_mt(f3(ldg4(tp + 0)), f3(ldg4(tp + 1)), f3(ldg4(tp + 2)), o, d);
+    if (t >= 0.0f && t < *best_t && tri_gate(sc, o, inv, i)) { *best_t = t; *best = i; }
+  }
+}
+
 // Candidates every ray tests in a fixed order, with the reference's exact arithmetic and its leaf-AABB gate:
 // the spheres (no culling at all: the r = 1e5 ground sphere of scenes/primitive.toml has a t error far larger
 // than any box slack), then the flat list of large triangles tris[n_bvh_tris, n_tris) (bvh_build.cpp).
@@ -161,17 +179,23 @@ LR_DEV void flat_hits(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, int
       if (ref_slab_pass(c - r, c + r, o, inv)) { best_t = t; best = -2 - i; }
     }
   }
+  // flat triangles: optimistic pass (accept the nearest candidate ungated), then ONE gate test on the winner; if the
+  // gate rejects it (fp corner cases, hits beyond t = 1e5) the list is re-run with the gate on every candidate.  If the
+  // winner passes it is the gated nearest hit (the minimum over a superset that lies in the subset, same order).
+  const float t_sph = best_t;
+  const int b_sph = best;
+#pragma unroll 1
   for (int i = sc.n_bvh_tris; i < sc.n_tris; i++) {
     const float4* tp = sc.tris + 3 * (size_t)i;
     const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
     if (COUNT) tc.tris++;
-    const F3 p0 = f3(v0), p1 = f3(v1), p2 = f3(v2);
-    const float t = triangle_mt(p0, p1, p2, o, d);
-    if (t >= 0.0f && t < best_t) {
-      const F3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
-      const F3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
-      if (ref_slab_pass(lo, hi, o, inv)) { best_t = t; best = i; }
-    }
+    const float t = triangle_mt(f3(v0), f3(v1), f3(v2), o, d);
+    if (t >= 0.0f && t < best_t) { best_t = t; best = i; }
+  }
+  if (best != b_sph && !tri_gate(sc, o, inv, best)) {
+    best_t = t_sph;
+    best = b_sph;
+    flat_tris_strict(sc, o, d, inv, &best_t, &best);
   }
 }
 
@@ -263,15 +287,7 @@ LR_DEV void bvh_traverse(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, 
   }
 }
 
-// the reference's gate (aabb.rs:75-92 on the triangle's own box, as Leaf::may_intersect applies it) for one BVH hit
-LR_DEV bool bvh_hit_is_gated(const DevScene& sc, F3 o, F3 inv, int id) {
-  const float4* tp = sc.tris + 3 * (size_t)id;
-  const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
-  const F3 p0 = f3(v0), p1 = f3(v1), p2 = f3(v2);
-  const F3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
-  const F3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
-  return ref_slab_pass(lo, hi, o, inv);
-}
+LR_DEV bool bvh_hit_is_gated(const DevScene& sc, F3 o, F3 inv, int id) { return tri_gate(sc, o, inv, id); }
 
 // Nearest hit: flat candidates first, then the BVH (strict `<`, so on exact ties the earlier candidate stays).
 template <bool COUNT>
@@ -296,11 +312,9 @@ LR_DEV Surface surface_at(const DevScene& sc, F3 o, F3 d, float t, int id) {
   s.pos = o + d * t;
   if (id >= 0) {
     const float4* tp = sc.tris + 3 * (size_t)id;
-    const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
-    const F3 p0 = f3(v0), p1 = f3(v1), p2 = f3(v2);
-    s.n = normalize(cross(p1 - p0, p2 - p0));          // triangle.rs:36
-    s.prim = __float_as_int(v0.w);
-    s.mat = __float_as_int(v1.w);
+    s.n = f3(ldg4(sc.tri_n + id));                     // triangle.rs:36, computed once at upload like Triangle::new
+    s.prim = __float_as_int(ldg4(tp + 0).w);
+    s.mat = __float_as_int(ldg4(tp + 1).w);
   } else {
     const int i = -2 - id;
     const float4 sp = ldg4(sc.spheres + i);
@@ -348,9 +362,20 @@ LR_DEV Mat load_mat(const DevScene& sc, int i) {
   return m;
 }
 
-LR_DEV float signed_mod(float base, float module) {                // lambert.rs:58-64
-  if (base > 0.0f) return fmodf(base, module);
-  return module - fmodf(-base, module);
+// fmodf(x, m) for x >= 0 and a positive module m (the checker's 30 / 150 / 300), exactly: q = trunc(fl(x / m)) is the
+// true integer quotient or one above it (an IEEE quotient never rounds below an integer that the true quotient
+// reaches), so r = x - q*m, computed without rounding by one FMA, is the remainder or the remainder minus m, and
+// both that value and the corrected one are multiples of ulp(m) below 2^24 ulps, i.e. exactly representable.
+// Checked against fmod over random and adversarial inputs in tests/test_host_frontend.py (same IEEE operations).
+LR_DEV float fmod_pos(float x, float m) {
+  if (!(x < m * 8388608.0f)) return fmodf(x, m);                   // quotient beyond 2^23: the library routine (also NaN / inf)
+  const float q = truncf(x / m);
+  const float r = __fmaf_rn(-q, m, x);
+  return r < 0.0f ? r + m : r;
+}
+LR_DEV float signed_mod(float base, float module) {                // lambert.rs:58-64  (base % module on |base|)
+  const float r = fmod_pos(fabsf(base), module);
+  return base > 0.0f ? r : module - r;
 }
 LR_DEV float checker(float u, float v) {                           // lambert.rs:66-90 (grey value)
   const float lw = 2.0f, li = 150.0f, sw = 1.0f, si = 30.0f, cw = 150.0f, ci = 300.0f;

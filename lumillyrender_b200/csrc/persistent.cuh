@@ -55,8 +55,19 @@ __device__ __noinline__ void trace_strict(const DevScene& sc, F3 o, F3 d, float*
 
 }  // namespace pk
 
-template <int INTEGRATOR, bool COUNT>
-__global__ void __launch_bounds__(kBlockThreads)
+// Resident CTAs per SM asked of the register allocator, by integrator and by whether the scene has a BVH (TREE).
+// Measured A/B on one box (profiles/r01_c_ab_s16.txt, s17): the pt-direct kernel (96 registers uncapped) gains 27 % on
+// welcome-2018 when capped so that 12 CTAs fit (its tree traversal is latency bound and likes warps) but loses 15 % on
+// the flat-only brdf scene (pure arithmetic, the spills hurt); the pt kernel (80 registers) is fastest uncapped on
+// sample.toml and 10 % faster capped to 8 CTAs on the spheres-only primitive.toml.
+template <int INTEGRATOR, bool TREE>
+struct MinBlocks {
+  static constexpr int value = INTEGRATOR == LR_INTEGRATOR_PT_DIRECT ? (TREE ? 12 : 6) : (TREE ? 1 : 8);
+};
+
+// TREE = false: the scene has no BVH (spheres and flat triangles only); phase B is compiled out.
+template <int INTEGRATOR, bool TREE, bool COUNT>
+__global__ void __launch_bounds__(kBlockThreads, MinBlocks<INTEGRATOR, TREE>::value)
 render_persistent_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ DevParams p, float* __restrict__ out_sum,
                          float* __restrict__ out_sumsq, unsigned long long* __restrict__ counters, unsigned int* __restrict__ next_unit) {
   using namespace pk;
@@ -284,7 +295,7 @@ render_persistent_kernel(const __grid_constant__ DevScene sc, const __grid_const
           int id = -1;
           flat_hits<COUNT>(sc, o, d, inv, t, id, tc);
           n_rays++;
-          const bool pd = sc.n_nodes > 0 && bvh_bounds_hit(sc, o, inv, t < 3.0e38f ? t * 1.0001f + 1e-4f : 3.0e38f);
+          const bool pd = TREE && sc.n_nodes > 0 && bvh_bounds_hit(sc, o, inv, t < 3.0e38f ? t * 1.0001f + 1e-4f : 3.0e38f);
           if (r == 0) { t0 = t; id0 = id; pend0 = pd; } else { t1 = t; id1 = id; pend1 = pd; }
         }
       }
@@ -295,7 +306,7 @@ render_persistent_kernel(const __grid_constant__ DevScene sc, const __grid_const
     // the suspended rays traverse the BVH together (one call site): optimistic accept, the nearest hit gated once at
     // the end, strict re-trace in the rare case the gate rejects it
 #pragma unroll 1
-    for (int r = 0; r < NR; r++) {
+    for (int r = 0; TREE && r < NR; r++) {
       const bool on = r == 0 ? pend0 : pend1;
       if (!__any_sync(kFull, on)) continue;
       if (on) {
@@ -332,16 +343,16 @@ render_persistent_kernel(const __grid_constant__ DevScene sc, const __grid_const
 }
 
 // one launch = the whole sample range of every unit: a persistent grid that fills the SMs
-template <int INTEGRATOR, bool COUNT>
+template <int INTEGRATOR, bool TREE, bool COUNT>
 cudaError_t launch_persistent_one(const DevScene& sc, const DevParams& p, float* out_sum, float* out_sumsq,
                                   unsigned long long* counters, unsigned int* next_unit, int sm_count, cudaStream_t stream) {
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_persistent_kernel<INTEGRATOR, COUNT>, kBlockThreads, 0) !=
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_persistent_kernel<INTEGRATOR, TREE, COUNT>, kBlockThreads, 0) !=
           cudaSuccess || nb <= 0) nb = 4;
   const long long units = (long long)p.tiles_x * p.tiles_y * 32 * p.splits;
   const long long want = (units + kBlockThreads - 1) / kBlockThreads;
   const unsigned int blocks = (unsigned int)std::max<long long>(1, std::min<long long>(want, (long long)nb * sm_count));
-  render_persistent_kernel<INTEGRATOR, COUNT><<<blocks, kBlockThreads, 0, stream>>>(sc, p, out_sum, out_sumsq, counters, next_unit);
+  render_persistent_kernel<INTEGRATOR, TREE, COUNT><<<blocks, kBlockThreads, 0, stream>>>(sc, p, out_sum, out_sumsq, counters, next_unit);
   return cudaGetLastError();
 }
 

@@ -215,3 +215,40 @@ def test_counters_instrumented_traversal(scenes):
     assert np.array_equal(a, b)
     assert st0["nodes_visited"] == 0 and st1["nodes_visited"] > st1["rays"] and st1["tris_tested"] > 0
     assert st0["rays"] == st1["rays"]
+
+
+def test_gate_retrace_and_flat_list(lr, orc, gpu):
+    """Triangles beyond t = 1e5 are invisible in the reference (the AABB line test is clipped to +-1e5, aabb.rs:76-77).
+    The render kernel accepts BVH hits optimistically and gates the nearest one once: here the gate must reject it
+    and the strict re-trace must answer like the oracle.  A wall-sized triangle exercises the flat list the same way."""
+    from lumillyrender_b200 import capi
+    rng = np.random.RandomState(3)
+    far = (rng.normal(0, 1, (60, 3, 3)) * 2.0e4 + np.array([0, 0, -1.5e5]) + rng.uniform(-6e4, 6e4, (60, 1, 3)) * [1, 1, 0]).astype(np.float32)
+    near = _soup(rng, 40, scale=6.0, size=1.5)
+    wall = np.array([[[-3e5, -3e5, -2.0e5], [3e5, -3e5, -2.0e5], [0, 4e5, -2.0e5]]], dtype=np.float32)    # large: goes to the flat list
+    tri = np.concatenate([near, far, wall])
+    d = _scene_from_tris(lr, tri)
+    desc = d.desc.contents
+    assert 1 <= desc.n_flat_triangles < len(tri) and desc.n_nodes > 0
+    desc.sky.type = capi.LR_SKY_UNIFORM
+    desc.sky.color[:] = [1.0, 0.9, 0.8]
+    s = d.scene()
+    o = orc.OracleScene(d.desc, keepalive=d)
+    # nearest hits of rays aimed at the far triangles and the wall: invisible, like the oracle's brute force says
+    n = 4000
+    org = np.zeros((n, 3), np.float32) + np.array([0, 0, 40], np.float32)
+    k = rng.randint(len(near), len(tri), n)
+    w = rng.dirichlet([1, 1, 1], n).astype(np.float32)
+    dirs = (tri[k] * w[:, :, None]).sum(1) - org
+    dirs = (dirs / np.linalg.norm(dirs, axis=1, keepdims=True)).astype(np.float32)
+    pg, tg, _ = s.trace_rays(org, dirs, normals=True)
+    po, to, _ = o.trace_rays(org, dirs, brute_force=True)
+    assert np.array_equal(pg, po) and np.array_equal(tg[po >= 0], to[po >= 0])
+    assert (po < len(near)).all(), "nothing beyond t = 1e5 may be hit"
+    # the render path: same image as the oracle's replay, and the gate did fire
+    img, _, st = s.render(integrator="pt", spp=4, seed=9, splits=1, depth=5, depth_limit=64, no_direct_emitter=0)
+    ref_sum, _, ost = o.render(make_params(lr, d.config, integrator=0, spp=4, seed=9, depth=5, depth_limit=64, no_direct_emitter=0),
+                               traversal=0, rng_mode=0, math_mode=1)
+    assert st["rays"] == ost["rays"]
+    assert np.isclose(img, ref_sum / 4, rtol=1e-4, atol=1e-5).all(-1).mean() >= 0.999
+    assert st["gate_retraces"] > 0, "the far triangles must have been found optimistically and rejected by the gate"

@@ -5,10 +5,15 @@ import csv, io, os, re, subprocess, sys, tempfile, glob, collections
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 45
-tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "lumillyrender_b200", "liblumilly_b200.so")], cwd=tmp, capture_output=True)
-cub = [c for c in glob.glob(tmp + "/*.cubin") if os.path.basename(c).startswith(os.environ.get("CUBIN_PREFIX", "kernels.sm"))][0]
-dis = subprocess.run(["nvdisasm", "--print-line-info", cub], capture_output=True, text=True).stdout.splitlines()
+# every object of the in-tree build holds one cubin; disassemble them all and keep the one with the kernel
+dis = []
+for obj in sorted(glob.glob(os.path.join(ROOT, "lumillyrender_b200", "build", "*.o"))):
+    tmp = tempfile.mkdtemp()
+    subprocess.run(["cuobjdump", "-xelf", "all", obj], cwd=tmp, capture_output=True)
+    for cub in glob.glob(tmp + "/*.cubin"):
+        out = subprocess.run(["nvdisasm", "--print-line-info", cub], capture_output=True, text=True).stdout
+        if kern in out:
+            dis = out.splitlines()
 line_of, cur, inside = {}, None, False
 for l in dis:
     if l.startswith(".text."):

@@ -21,7 +21,7 @@ for cfg in sys.argv[1:]:
     for k in keys:
         os.environ.pop(k, None)
     for kv in cfg.split(","):
-        if kv:
+        if "=" in kv:
             k, v = kv.split("=")
             os.environ[k] = v
             keys.add(k)

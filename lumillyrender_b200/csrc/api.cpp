@@ -117,13 +117,20 @@ int lr_scene_create(const LrSceneDesc* d, LrScene** out) {
   // ---- pack host-side arrays (layout documented in device_scene.h)
   std::vector<float4> nodes((size_t)d->n_nodes * 4), tris((size_t)d->n_triangles * 3), spheres(d->n_spheres), mats((size_t)d->n_materials * 3);
   std::vector<int2> sphere_meta(d->n_spheres);
-  std::vector<float4> tri_n(d->n_triangles);
+  std::vector<float4> tri_n(d->n_triangles), tri_box((size_t)d->n_triangles * 2);
   std::memcpy(nodes.data(), d->nodes, (size_t)d->n_nodes * sizeof(LrBvhNode));
   for (int i = 0; i < d->n_triangles; i++) {
     const LrTriangle& t = d->triangles[i];
+    // p0 and the edges of Moller-Trumbore, e1 = p1 - p0, e2 = p2 - p0 (triangle.rs:71-72): single fp32 subtractions
+    const Vec3 e1 = vsub(vec3(t.p1), vec3(t.p0)), e2 = vsub(vec3(t.p2), vec3(t.p0));
     tris[3 * (size_t)i + 0] = mk4(t.p0[0], t.p0[1], t.p0[2], as_float(t.prim_id));
-    tris[3 * (size_t)i + 1] = mk4(t.p1[0], t.p1[1], t.p1[2], as_float(t.material));
-    tris[3 * (size_t)i + 2] = mk4(t.p2[0], t.p2[1], t.p2[2], 0.0f);
+    tris[3 * (size_t)i + 1] = mk4(e1[0], e1[1], e1[2], as_float(t.material));
+    tris[3 * (size_t)i + 2] = mk4(e2[0], e2[1], e2[2], 0.0f);
+    // Triangle::aabb (triangle.rs:102-119): min / max of the vertices
+    tri_box[2 * (size_t)i + 0] = mk4(std::fmin(std::fmin(t.p0[0], t.p1[0]), t.p2[0]), std::fmin(std::fmin(t.p0[1], t.p1[1]), t.p2[1]),
+                                     std::fmin(std::fmin(t.p0[2], t.p1[2]), t.p2[2]), 0.0f);
+    tri_box[2 * (size_t)i + 1] = mk4(std::fmax(std::fmax(t.p0[0], t.p1[0]), t.p2[0]), std::fmax(std::fmax(t.p0[1], t.p1[1]), t.p2[1]),
+                                     std::fmax(std::fmax(t.p0[2], t.p1[2]), t.p2[2]), 0.0f);
     // triangle.rs:36  normal = (p1 - p0).cross(p2 - p0).normalize(), in the reference's fp32 operation order
     const Vec3 n = vnormalize(vcross(vsub(vec3(t.p1), vec3(t.p0)), vsub(vec3(t.p2), vec3(t.p0))));
     tri_n[i] = mk4(n[0], n[1], n[2], 0.0f);
@@ -191,6 +198,7 @@ int lr_scene_create(const LrSceneDesc* d, LrScene** out) {
   if (e == cudaSuccess) { e = upload(nodes, &dv.nodes, s->h2d_bytes); track(dv.nodes); }
   if (e == cudaSuccess) { e = upload(tris, &dv.tris, s->h2d_bytes); track(dv.tris); }
   if (e == cudaSuccess) { e = upload(tri_n, &dv.tri_n, s->h2d_bytes); track(dv.tri_n); }
+  if (e == cudaSuccess) { e = upload(tri_box, &dv.tri_box, s->h2d_bytes); track(dv.tri_box); }
   if (e == cudaSuccess) { e = upload(spheres, &dv.spheres, s->h2d_bytes); track(dv.spheres); }
   if (e == cudaSuccess) { e = upload(sphere_meta, &dv.sphere_meta, s->h2d_bytes); track(dv.sphere_meta); }
   if (e == cudaSuccess) { e = upload(mats, &dv.mats, s->h2d_bytes); track(dv.mats); }

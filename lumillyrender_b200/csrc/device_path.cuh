@@ -108,10 +108,9 @@ LR_DEV bool ref_slab_pass(F3 lo, F3 hi, F3 o, F3 inv) {
 }
 
 // ------------------------------------------------------------------ primitive tests
-// triangle.rs:69-100.  Returns t or a negative value for a miss.
-LR_DEV float triangle_mt(F3 p0, F3 p1, F3 p2, F3 o, F3 d) {
-  const F3 e1 = p1 - p0;
-  const F3 e2 = p2 - p0;
+// triangle.rs:69-100.  Returns t or a negative value for a miss.  The edges e1 = p1 - p0, e2 = p2 - p0 (triangle.rs:71-72)
+// are single fp32 subtractions, so they are computed once at upload (api.cpp) instead of once per test: same bits.
+LR_DEV float triangle_mt(F3 p0, F3 e1, F3 e2, F3 o, F3 d) {
   const F3 pv = cross(d, e2);
   const float det = dot(e1, pv);
   if (fabsf(det) < kEPS) return -1.0f;
@@ -146,13 +145,10 @@ struct TraceCounters { unsigned int nodes, tris, spheres; };
 LR_DEV float4 ldg4(const float4* p) { return __ldg(p); }
 
 // the reference's gate (aabb.rs:75-92 on the triangle's own box, as Leaf::may_intersect applies it, bvh.rs:21-25)
+// (the box is the min / max of the vertices, triangle.rs:102-119: exact operations, stored at upload in tri_box)
 LR_DEV bool tri_gate(const DevScene& sc, F3 o, F3 inv, int id) {
-  const float4* tp = sc.tris + 3 * (size_t)id;
-  const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
-  const F3 p0 = f3(v0), p1 = f3(v1), p2 = f3(v2);
-  const F3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
-  const F3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
-  return ref_slab_pass(lo, hi, o, inv);
+  const float4* bp = sc.tri_box + 2 * (size_t)id;
+  return ref_slab_pass(f3(ldg4(bp + 0)), f3(ldg4(bp + 1)), o, inv);
 }
 // flat triangle list with the gate on every candidate (the rare fallback of flat_hits), out of line
 static __device__ __noinline__ void flat_tris_strict(const DevScene& sc, F3 o, F3 d, F3 inv, float* best_t, int* best) {
@@ -265,17 +261,10 @@ LR_DEV void bvh_traverse(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, 
         const float4* tp = sc.tris + 3 * (size_t)(first + k);
         const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
         if (COUNT) tc.tris++;
-        const F3 p0 = f3(v0), p1 = f3(v1), p2 = f3(v2);
-        const float t = triangle_mt(p0, p1, p2, o, d);
+        const float t = triangle_mt(f3(v0), f3(v1), f3(v2), o, d);
         if (t >= 0.0f && t < best_t) {
-          bool ok = true;
-          if (STRICT) {
-            // the leaf's own AABB gate (triangle.rs:102-119 box, aabb.rs:75-92 test)
-            const F3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
-            const F3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
-            ok = ref_slab_pass(lo, hi, o, inv);
-          }
-          if (ok) {
+          // STRICT: the leaf's own AABB gate (triangle.rs:102-119 box, aabb.rs:75-92 test)
+          if (!STRICT || tri_gate(sc, o, inv, first + k)) {
             best_t = t;
             best = first + k;
             cull_t = best_t * 1.0001f + 1e-4f;

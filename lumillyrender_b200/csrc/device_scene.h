@@ -3,8 +3,9 @@
 // Everything the kernels read is a flat, 16-byte aligned array so that every fetch on the
 // traversal path is a 128-bit load:
 //   nodes    : 4 x float4 per BVH node   (64 B)   — two child boxes + child codes
-//   tris     : 3 x float4 per triangle   (48 B)   — p0|prim_id, p1|material, p2|0   (BVH leaf order, then
-//                                                   the flat list of large triangles every ray tests)
+//   tris     : 3 x float4 per triangle   (48 B)   — p0|prim_id, e1 = p1-p0|material, e2 = p2-p0|0   (BVH leaf order,
+//                                                   then the flat list of large triangles every ray tests)
+//   tri_box  : 2 x float4 per triangle   (32 B)   — box of the vertices (cold: read once per ray, for the gate)
 //   tri_n    : 1 x float4 per triangle   (16 B)   — unit geometric normal | 0 (read once per path vertex)
 //   spheres  : 1 x float4 per sphere     (16 B)   — centre|radius     (+ int2 material/prim_id)
 //   mats     : 3 x float4 per material   (48 B)   — colour|type, emission|param0, param1|weight|emissive|0
@@ -23,6 +24,7 @@ constexpr int kBlockThreads = 128;       // 4 warps, each warp owns an 8x4 pixel
 struct DevScene {
   const float4* nodes;
   const float4* tris;
+  const float4* tri_box;                 // 2 x float4 per triangle: box lo | hi of the vertices (the reference's leaf-AABB gate)
   const float4* tri_n;                   // geometric normal per triangle, precomputed like Triangle::new does (triangle.rs:36)
   const float4* spheres;
   const int2* sphere_meta;

@@ -15,6 +15,15 @@
 namespace lr {
 
 #define LR_DEV __device__ __forceinline__
+// Code that most scenes never run (IBL lookup, Phong / Blinn-Phong / refraction, lens cameras, library fmodf) is kept out
+// of line when LR_OUTLINE_COLD is set (build.py sets it for the render kernel): the kernel is instruction-fetch bound and
+// every inlined cold branch dilutes the hot code (profiles/r01_c_ab_s23.txt).  Arguments go by value so that no hot
+// variable has its address taken.
+#ifdef LR_OUTLINE_COLD
+#define LR_COLD static __device__ __noinline__
+#else
+#define LR_COLD __device__ __forceinline__
+#endif
 
 constexpr float kPI = 3.14159265358979323846264338327950288f;   // constant.rs:1
 constexpr float kEPS = 1e-3f;                                   // constant.rs:2
@@ -31,7 +40,16 @@ LR_DEV F3 operator-(F3 a, F3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
 LR_DEV F3 operator*(F3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
 LR_DEV F3 operator*(float s, F3 a) { return f3(s * a.x, s * a.y, s * a.z); }
 LR_DEV F3 operator*(F3 a, F3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+// IEEE quotient of a vector by a scalar.  In the kernels that traverse a BVH the three divisions live in ONE out-of-line
+// function (LR_DIV_OUT_OF_LINE, set by build.py for those translation units): ~20 inlined copies of 3 x 14 instructions
+// are a fifth of the kernel's code, and the kernel is instruction-fetch bound (A/B, profiles/r01_c_ab_s22.txt: +4.6 % on
+// sample.toml; the flat-only kernels are 3 % faster with the divisions inlined).
+#ifdef LR_DIV_OUT_OF_LINE
+static __device__ __noinline__ F3 div3_call(F3 a, float s) { F3 r; r.x = a.x / s; r.y = a.y / s; r.z = a.z / s; return r; }
+LR_DEV F3 operator/(F3 a, float s) { return div3_call(a, s); }
+#else
 LR_DEV F3 operator/(F3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+#endif
 LR_DEV float dot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 LR_DEV F3 cross(F3 a, F3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 LR_DEV float sqr_norm(F3 a) { return dot(a, a); }
@@ -356,8 +374,9 @@ LR_DEV Mat load_mat(const DevScene& sc, int i) {
 // reaches), so r = x - q*m, computed without rounding by one FMA, is the remainder or the remainder minus m, and
 // both that value and the corrected one are multiples of ulp(m) below 2^24 ulps, i.e. exactly representable.
 // Checked against fmod over random and adversarial inputs in tests/test_host_frontend.py (same IEEE operations).
+LR_COLD float fmodf_cold(float x, float m) { return fmodf(x, m); }
 LR_DEV float fmod_pos(float x, float m) {
-  if (!(x < m * 8388608.0f)) return fmodf(x, m);                   // quotient beyond 2^23: the library routine (also NaN / inf)
+  if (!(x < m * 8388608.0f)) return fmodf_cold(x, m);                   // quotient beyond 2^23: the library routine (also NaN / inf)
   const float q = truncf(x / m);
   const float r = __fmaf_rn(-q, m, x);
   return r < 0.0f ? r + m : r;
@@ -399,6 +418,40 @@ LR_DEV float fresnel_exact(float n1, float n2, F3 out_, F3 in_, F3 on) {        
   return (a * a + b * b) / 2.0f;
 }
 
+// Material::brdf of Phong, Blinn-Phong and ideal refraction
+LR_COLD F3 mat_brdf_other(int type, F3 color, float param0, float param1, F3 out_, F3 in_, F3 n) {
+  if (type == LR_MAT_PHONG) {                                      // phong.rs:39-47
+    const F3 on = orienting_normal(out_, n);
+    if (dot(in_, on) <= 0.0f) return f3(0.0f, 0.0f, 0.0f);
+    const F3 r = reflect(out_, on);
+    const float c = dot(r, in_);
+    const float a = param0;
+    return color * ((a + 2.0f) / (2.0f * kPI) * powf(c, a));
+  }
+  if (type == LR_MAT_BLINN_PHONG) {                                // blinn_phong.rs:39-49
+    const F3 on = orienting_normal(out_, n);
+    if (dot(in_, on) <= 0.0f) return f3(0.0f, 0.0f, 0.0f);
+    const F3 h = normalize(in_ + out_);
+    const float c = dot(h, on);
+    const float a = param0;
+    return color * ((a + 2.0f) * (a + 4.0f) / (8.0f * kPI * (powf(2.0f, -a / 2.0f) + a)) * powf(c, a));
+  }
+  {                                                                // ideal_refraction.rs:40-68
+    const F3 on = orienting_normal(out_, n);
+    float from_ior, to_ior;
+    if (dot(out_, n) > 0.0f) { from_ior = 1.0f; to_ior = param1; } else { from_ior = param1; to_ior = 1.0f; }   // ior_pair
+    F3 r;
+    if (refract(out_, on, from_ior / to_ior, r)) {
+      const float fr = fresnel_exact(from_ior, to_ior, out_, r, on);
+      if (dot(in_, on) > 0.0f) return color * 1.0f / dot(in_, n) * fr;
+      const float q = to_ior / from_ior;
+      const float ft = (1.0f - fr) * (q * q);
+      return color * 1.0f / dot(in_, n) * ft;
+    }
+    return color * 1.0f / dot(in_, n);
+  }
+}
+
 // Material::brdf
 LR_DEV F3 mat_brdf(const Mat& m, F3 out_, F3 in_, F3 n, F3 pos) {
   if (m.type == LR_MAT_LAMBERT) {                                  // lambert.rs:32-35
@@ -418,50 +471,52 @@ LR_DEV F3 mat_brdf(const Mat& m, F3 out_, F3 in_, F3 n, F3 pos) {
     const float d = ggx_ndf(a2, h, on);
     return m.color * f * g * d / (4.0f * dot(in_, on) * dot(out_, on));
   }
-  if (m.type == LR_MAT_PHONG) {                                    // phong.rs:39-47
-    const F3 on = orienting_normal(out_, n);
-    if (dot(in_, on) <= 0.0f) return f3(0.0f, 0.0f, 0.0f);
+  return mat_brdf_other(m.type, m.color, m.param0, m.param1, out_, in_, n);
+}
+
+// Material::sample of ideal refraction (one draw) and of Phong / Blinn-Phong (xi2 and the sin / cos of 2 pi xi1 drawn by the caller)
+LR_COLD void mat_sample_refraction(float ior, F3 out_, F3 n, F3 on, unsigned long long rng_state, unsigned long long* rng_out,
+                                   F3* in_, float* pdf) {          // ideal_refraction.rs:70-104
+  Pcg rng;
+  rng.state = rng_state;
+  float from_ior, to_ior;
+  if (dot(out_, n) > 0.0f) { from_ior = 1.0f; to_ior = ior; } else { from_ior = ior; to_ior = 1.0f; }
+  F3 r;
+  if (refract(out_, on, from_ior / to_ior, r)) {
+    const float fr = fresnel_exact(from_ior, to_ior, out_, r, on);
+    if (rng.next() < fr) { *in_ = reflect(out_, on); *pdf = 1.0f * fr; }
+    else { *in_ = r; *pdf = 1.0f * (1.0f - fr); }
+  } else { *in_ = reflect(out_, on); *pdf = 1.0f; }
+  *rng_out = rng.state;
+}
+LR_COLD void mat_sample_phong_blinn(int type, float a, F3 out_, F3 on, float xi2, float s1, float c1, F3* in_, float* pdf) {
+  if (type == LR_MAT_PHONG) {                                      // phong.rs:49-69
     const F3 r = reflect(out_, on);
-    const float c = dot(r, in_);
-    const float a = m.param0;
-    return m.color * ((a + 2.0f) / (2.0f * kPI) * powf(c, a));
-  }
-  if (m.type == LR_MAT_BLINN_PHONG) {                              // blinn_phong.rs:39-49
-    const F3 on = orienting_normal(out_, n);
-    if (dot(in_, on) <= 0.0f) return f3(0.0f, 0.0f, 0.0f);
-    const F3 h = normalize(in_ + out_);
-    const float c = dot(h, on);
-    const float a = m.param0;
-    return m.color * ((a + 2.0f) * (a + 4.0f) / (8.0f * kPI * (powf(2.0f, -a / 2.0f) + a)) * powf(c, a));
-  }
-  {                                                                // ideal_refraction.rs:40-68
-    const F3 on = orienting_normal(out_, n);
-    float from_ior, to_ior;
-    ior_pair(m, out_, n, from_ior, to_ior);
-    F3 r;
-    if (refract(out_, on, from_ior / to_ior, r)) {
-      const float fr = fresnel_exact(from_ior, to_ior, out_, r, on);
-      if (dot(in_, on) > 0.0f) return m.color * 1.0f / dot(in_, n) * fr;
-      const float q = to_ior / from_ior;
-      const float ft = (1.0f - fr) * (q * q);
-      return m.color * 1.0f / dot(in_, n) * ft;
-    }
-    return m.color * 1.0f / dot(in_, n);
+    F3 u, v;
+    orthonormal_basis(r, u, v);
+    const float t = powf(xi2, 1.0f / (a + 2.0f));
+    const float ts = sqrtf(1.0f - t * t);
+    *in_ = u * c1 * ts + v * s1 * ts + r * t;
+    *pdf = (a + 2.0f) / (2.0f * kPI) * powf(dot(r, *in_), a);
+  } else {                                                         // blinn_phong.rs:51-73
+    F3 u, v;
+    orthonormal_basis(on, u, v);
+    const float t = powf(xi2, 1.0f / (a + 2.0f));
+    const float ts = sqrtf(1.0f - t * t);
+    const F3 h = u * c1 * ts + v * s1 * ts + on * t;
+    *in_ = h * (2.0f * dot(out_, h)) - out_;
+    *pdf = (a + 2.0f) / (2.0f * kPI) * powf(dot(on, h), a);
   }
 }
 
 // Material::sample (draw order as the reference)
 LR_DEV void mat_sample(const Mat& m, F3 out_, F3 n, Pcg& rng, F3& in_, float& pdf) {
   const F3 on = orienting_normal(out_, n);
-  if (m.type == LR_MAT_IDEAL_REFRACTION) {                         // ideal_refraction.rs:70-104
-    float from_ior, to_ior;
-    ior_pair(m, out_, n, from_ior, to_ior);
-    F3 r;
-    if (refract(out_, on, from_ior / to_ior, r)) {
-      const float fr = fresnel_exact(from_ior, to_ior, out_, r, on);
-      if (rng.next() < fr) { in_ = reflect(out_, on); pdf = 1.0f * fr; }
-      else { in_ = r; pdf = 1.0f * (1.0f - fr); }
-    } else { in_ = reflect(out_, on); pdf = 1.0f; }
+  if (m.type == LR_MAT_IDEAL_REFRACTION) {
+    F3 wi; float pd;
+    unsigned long long st;
+    mat_sample_refraction(m.param1, out_, n, on, rng.state, &st, &wi, &pd);
+    rng.state = st; in_ = wi; pdf = pd;
     return;
   }
   const float xi1 = rng.next();
@@ -494,36 +549,18 @@ LR_DEV void mat_sample(const Mat& m, F3 out_, F3 n, Pcg& rng, F3& in_, float& pd
     pdf = ggx_ndf(a2, h, on) * dot(h, on) * jacobian;
     return;
   }
-  if (m.type == LR_MAT_PHONG) {                                    // phong.rs:49-69
-    const float a = m.param0;
-    const F3 r = reflect(out_, on);
-    F3 u, v;
-    orthonormal_basis(r, u, v);
-    const float t = powf(xi2, 1.0f / (a + 2.0f));
-    const float ts = sqrtf(1.0f - t * t);
-    in_ = u * c1 * ts + v * s1 * ts + r * t;
-    pdf = (a + 2.0f) / (2.0f * kPI) * powf(dot(r, in_), a);
-    return;
-  }
-  {                                                                // blinn_phong.rs:51-73
-    const float a = m.param0;
-    F3 u, v;
-    orthonormal_basis(on, u, v);
-    const float t = powf(xi2, 1.0f / (a + 2.0f));
-    const float ts = sqrtf(1.0f - t * t);
-    const F3 h = u * c1 * ts + v * s1 * ts + on * t;
-    in_ = h * (2.0f * dot(out_, h)) - out_;
-    pdf = (a + 2.0f) / (2.0f * kPI) * powf(dot(on, h), a);
-    return;
-  }
+  F3 wi; float pd;
+  mat_sample_phong_blinn(m.type, m.param0, out_, on, xi2, s1, c1, &wi, &pd);
+  in_ = wi; pdf = pd;
 }
 
 // Material::coef (traits.rs:20-22; ideal_refraction.rs:106-113)
+LR_COLD F3 beer_absorption(F3 color, float absorbtance, float fly_distance) {     // ideal_refraction.rs:106-113
+  const F3 v = -(f3(1.0f, 1.0f, 1.0f) - color) * absorbtance * fly_distance;
+  return f3(expf(v.x), expf(v.y), expf(v.z));
+}
 LR_DEV F3 mat_coef(const Mat& m, F3 out_, F3 n, float fly_distance) {
-  if (m.type == LR_MAT_IDEAL_REFRACTION && dot(out_, n) < 0.0f) {
-    const F3 v = -(f3(1.0f, 1.0f, 1.0f) - m.color) * m.param0 * fly_distance;
-    return f3(expf(v.x), expf(v.y), expf(v.z));
-  }
+  if (m.type == LR_MAT_IDEAL_REFRACTION && dot(out_, n) < 0.0f) return beer_absorption(m.color, m.param0, fly_distance);
   return f3(1.0f, 1.0f, 1.0f);
 }
 
@@ -533,19 +570,23 @@ LR_DEV unsigned long long f32_to_usize(float v) {   // Rust `as usize`: saturati
   if (v >= 1.8446744e19f) return 0xFFFFFFFFFFFFFFFFull;
   return (unsigned long long)v;
 }
-LR_DEV F3 sky_radiance(const DevScene& sc, F3 d) {
-  if (sc.sky_type == LR_SKY_UNIFORM) return f3(sc.sky_color);      // sky.rs:17-21
-  const float theta = acosf(d.y);                                  // sky.rs:57-79
+// IBLSky::radiance sky.rs:57-79: nearest texel of a 2H x H equirect image
+LR_COLD F3 sky_ibl(const float4* __restrict__ pixels, int sky_height, float longitude_offset, F3 d) {
+  const float theta = acosf(d.y);
   const float phi = atan2f(d.z, d.x);
-  const float u = fmodf((phi + kPI + sc.sky_longitude_offset) / (2.0f * kPI), 1.0f);
+  const float u = fmodf((phi + kPI + longitude_offset) / (2.0f * kPI), 1.0f);
   const float v = fmodf(theta / kPI, 1.0f);
-  const unsigned long long height = (unsigned long long)sc.sky_height;
+  const unsigned long long height = (unsigned long long)sky_height;
   const unsigned long long width = height * 2ull;
   const unsigned long long all = width * height;
   const unsigned long long x = f32_to_usize(floorf((float)width * u));
   const unsigned long long y = f32_to_usize(floorf((float)height * v));
   const unsigned long long index = y * width + x;
-  return f3(ldg4(sc.sky_pixels + (index % all)));
+  return f3(ldg4(pixels + (index % all)));
+}
+LR_DEV F3 sky_radiance(const DevScene& sc, F3 d) {
+  if (sc.sky_type == LR_SKY_UNIFORM) return f3(sc.sky_color);      // sky.rs:17-21
+  return sky_ibl(sc.sky_pixels, sc.sky_height, sc.sky_longitude_offset, d);
 }
 
 // ------------------------------------------------------------------ cameras (camera.rs)
@@ -607,6 +648,34 @@ LR_DEV void camera_sample(const LrCamera& c, int x, int y, Draw&& draw, F3& o, F
       g_term = cam_geometry_term(c, normalize(ap - sensor));
     }
     sens_over_pdf = c.sensor_sensitivity / (sensor_pdf * ap_pdf);
+  }
+}
+
+// camera.sample for the render kernel: the ideal pinhole inline, the lens cameras out of line
+LR_COLD void camera_sample_lens(const LrCamera* c, int x, int y, unsigned long long rng_state, unsigned long long* rng_out, F3* o, F3* d,
+                                float* g_term, float* sens_over_pdf) {
+  Pcg rng;
+  rng.state = rng_state;
+  F3 oo, dd;
+  float g, w;
+  camera_sample(*c, x, y, [&]() { return rng.next(); }, oo, dd, g, w);
+  *rng_out = rng.state; *o = oo; *d = dd; *g_term = g; *sens_over_pdf = w;
+}
+LR_DEV void camera_sample_rng(const LrCamera& c, int x, int y, Pcg& rng, F3& o, F3& d, float& g_term, float& sens_over_pdf) {
+  if (c.type == LR_CAM_IDEAL_PINHOLE) {                            // camera.rs:100-115
+    const float u = rng.next();
+    const float v = rng.next();
+    const F3 sensor = cam_sensor_point(c, x, y, u, v);
+    o = f3(c.aperture_position);
+    d = normalize(o - sensor);
+    g_term = 1.0f;
+    sens_over_pdf = c.sensor_sensitivity / (1.0f * 1.0f);
+  } else {
+    unsigned long long st;
+    F3 oo, dd;
+    float g, w;
+    camera_sample_lens(&c, x, y, rng.state, &st, &oo, &dd, &g, &w);
+    rng.state = st; o = oo; d = dd; g_term = g; sens_over_pdf = w;
   }
 }
 

@@ -95,8 +95,12 @@ __global__ void __launch_bounds__(256) read_bw_kernel(const float4* __restrict__
 // ------------------------------------------------------------------ launchers
 cudaError_t launch_render_persistent(const DevScene& sc, const DevParams& p, bool count, float* out_sum, float* out_sumsq,
                                      unsigned long long* counters, unsigned int* next_unit, int sm_count, cudaStream_t stream) {
-  if (p.integrator == LR_INTEGRATOR_PT) return launch_persistent_i0(sc, p, count, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
-  return launch_persistent_i1(sc, p, count, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
+  const bool tree = sc.n_nodes > 0 || count;     // the instrumented kernel exists in the tree units only
+  if (p.integrator == LR_INTEGRATOR_PT)
+    return tree ? launch_persistent_i0_t1(sc, p, count, out_sum, out_sumsq, counters, next_unit, sm_count, stream)
+                : launch_persistent_i0_t0(sc, p, count, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
+  return tree ? launch_persistent_i1_t1(sc, p, count, out_sum, out_sumsq, counters, next_unit, sm_count, stream)
+              : launch_persistent_i1_t0(sc, p, count, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
 }
 
 cudaError_t launch_reduce_splits(float* dst, const float* partial, size_t n, int splits, cudaStream_t stream) {

@@ -277,7 +277,7 @@ render_persistent_kernel(const __grid_constant__ DevScene sc, const __grid_const
         const int x = p.crop_x + lx, y = p.crop_y + ly;
         const unsigned int pixel = (unsigned int)(y * sc.cam.width + x);
         rng.seed(p.seed, pixel, (unsigned int)un.y);
-        camera_sample(sc.cam, x, y, [&]() { return rng.next(); }, o, d0, cam_g, cam_w);
+        camera_sample_rng(sc.cam, x, y, rng, o, d0, cam_g, cam_w);
         T = f3(1.0f, 1.0f, 1.0f);
         L = f3(0.0f, 0.0f, 0.0f);
         flags = (flags & ~(F_DEPTH_MASK | F_HAS_SHADOW)) | F_ALLOW_EMISSION | F_HAS_RAY;

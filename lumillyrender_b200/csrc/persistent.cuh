@@ -56,13 +56,24 @@ __device__ __noinline__ void trace_strict(const DevScene& sc, F3 o, F3 d, float*
 }  // namespace pk
 
 // Resident CTAs per SM asked of the register allocator, by integrator and by whether the scene has a BVH (TREE).
-// Measured A/B on one box (profiles/r01_c_ab_s16.txt, s17): the pt-direct kernel (96 registers uncapped) gains 27 % on
-// welcome-2018 when capped so that 12 CTAs fit (its tree traversal is latency bound and likes warps) but loses 15 % on
-// the flat-only brdf scene (pure arithmetic, the spills hurt); the pt kernel (80 registers) is fastest uncapped on
-// sample.toml and 10 % faster capped to 8 CTAs on the spheres-only primitive.toml.
+// Measured A/B on one box (profiles/r01_c_ab_s16.txt, s17, s24): the pt-direct tree kernel is latency bound and wants
+// warps (welcome-2018: 61.0 / 57.9 / 57.0 / 56.1 ms at 8 / 10 / 12 / 16 CTAs, spills and all), the flat-only pt-direct
+// kernel is pure arithmetic and wants registers (brdf: 25.1 / 23.7 / 22.7 ms at 8 / 6 / 4), the pt kernels sit between.
+#ifndef LR_MB_PT_TREE
+#define LR_MB_PT_TREE 6
+#endif
+#ifndef LR_MB_PT_FLAT
+#define LR_MB_PT_FLAT 8
+#endif
+#ifndef LR_MB_PTD_TREE
+#define LR_MB_PTD_TREE 16
+#endif
+#ifndef LR_MB_PTD_FLAT
+#define LR_MB_PTD_FLAT 4
+#endif
 template <int INTEGRATOR, bool TREE>
 struct MinBlocks {
-  static constexpr int value = INTEGRATOR == LR_INTEGRATOR_PT_DIRECT ? (TREE ? 12 : 6) : (TREE ? 1 : 8);
+  static constexpr int value = INTEGRATOR == LR_INTEGRATOR_PT_DIRECT ? (TREE ? LR_MB_PTD_TREE : LR_MB_PTD_FLAT) : (TREE ? LR_MB_PT_TREE : LR_MB_PT_FLAT);
 };
 
 // TREE = false: the scene has no BVH (spheres and flat triangles only); phase B is compiled out.

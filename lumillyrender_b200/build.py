@@ -57,8 +57,8 @@ def build_variant(name, defines):
 
 
 def build_library(force=False, verbose=False, extra=(), obj_dir=None):
-    """Compiles every translation unit to build/*.o in parallel (the render kernel is instantiated in four
-    units, integrator x scene-has-a-BVH, see csrc/persistent_inst.cu) and links liblumilly_b200.so."""
+    """Compiles every translation unit to build/*.o in parallel (the render kernel is instantiated in eight
+    units, integrator x scene-has-a-BVH x scene-has-GGX, see csrc/persistent_inst.cu) and links liblumilly_b200.so."""
     from concurrent.futures import ThreadPoolExecutor
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS + ["persistent_inst.cu"]] + [os.path.abspath(__file__)]
     if not force and not _stale(LIB, deps):
@@ -77,12 +77,15 @@ def build_library(force=False, verbose=False, extra=(), obj_dir=None):
         jobs.append(([_nvcc()] + flags + ["-c", os.path.join(CSRC, src), "-o", o], verbose))
     for integ in (0, 1):
         for tree in (0, 1):
-            o = os.path.join(obj_dir, "persistent_i%d_t%d.o" % (integ, tree))
-            objs.append(o)
-            defs = ["-DLR_INST_INTEGRATOR=%d" % integ, "-DLR_INST_TREE=%d" % tree] + (["-DLR_DIV_OUT_OF_LINE"] if tree else [])
-            if not os.environ.get("LR_NO_OUTLINE_COLD"):
-                defs.append("-DLR_OUTLINE_COLD")
-            jobs.append(([_nvcc()] + flags + defs + ["-c", os.path.join(CSRC, "persistent_inst.cu"), "-o", o], verbose))
+            for ggx in (0, 1):
+                o = os.path.join(obj_dir, "persistent_i%d_t%d_g%d.o" % (integ, tree, ggx))
+                objs.append(o)
+                defs = ["-DLR_INST_INTEGRATOR=%d" % integ, "-DLR_INST_TREE=%d" % tree, "-DLR_INST_GGX=%d" % ggx, "-DLR_OUTLINE_COLD"]
+                if tree:
+                    defs.append("-DLR_DIV_OUT_OF_LINE")
+                if not ggx:
+                    defs.append("-DLR_GGX_OUT_OF_LINE")
+                jobs.append(([_nvcc()] + flags + defs + ["-c", os.path.join(CSRC, "persistent_inst.cu"), "-o", o], verbose))
     with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
         list(ex.map(_compile, jobs))
     subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lz"], check=True)

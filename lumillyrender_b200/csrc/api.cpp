@@ -71,6 +71,7 @@ struct LrScene {
   mutable float acc_kernel_ms = 0.0f;
   mutable cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   mutable bool ev_pending = false;
+  bool has_ggx = false;                            // selects the render kernel built with GGX inline
 };
 
 extern "C" {
@@ -227,6 +228,7 @@ int lr_scene_create(const LrSceneDesc* d, LrScene** out) {
   dv.sky_longitude_offset = d->sky.longitude_offset;
   dv.cam = d->camera;
   s->width = d->camera.width; s->height = d->camera.height;
+  for (int i = 0; i < d->n_materials; i++) s->has_ggx = s->has_ggx || d->materials[i].type == LR_MAT_GGX;
   *out = s;
   return LR_OK;
 }
@@ -282,8 +284,8 @@ static int resolve_params(const LrScene* s, const LrRenderParams* p, DevParams& 
   // kernel organisation knobs (development / profiling only; defaults are the measured best)
   const char* e_di = std::getenv("LR_DEFER_ITERS");
   const char* e_dt = std::getenv("LR_DEFER_THRESH");
-  dp.defer_iters = e_di ? std::max(1, std::atoi(e_di)) : 4;
-  dp.defer_thresh = e_dt ? std::max(1, std::min(32, std::atoi(e_dt))) : 16;
+  dp.defer_iters = e_di ? std::max(1, std::atoi(e_di)) : 3;
+  dp.defer_thresh = e_dt ? std::max(1, std::min(32, std::atoi(e_dt))) : 12;
 
   return LR_OK;
 }
@@ -323,7 +325,7 @@ int lr_render_accumulate_device(const LrScene* s, const LrRenderParams* p, float
     // the unit cursor lives in the last word of the counter block (reset on the stream before every launch)
     unsigned int* next_unit = reinterpret_cast<unsigned int*>(s->d_counters + C_NEXT_UNIT);
     LR_CUDA(cudaMemsetAsync(next_unit, 0, sizeof(unsigned long long), st));
-    LR_CUDA(launch_render_persistent(s->dev, dp, p->count_traversal != 0, ksum, d_sumsq ? ksq : nullptr, s->d_counters, next_unit,
+    LR_CUDA(launch_render_persistent(s->dev, dp, s->has_ggx, p->count_traversal != 0, ksum, d_sumsq ? ksq : nullptr, s->d_counters, next_unit,
                                      std::max(g_sm_count, 1), st));
     s->acc_launches++;
   }

@@ -452,25 +452,50 @@ LR_COLD F3 mat_brdf_other(int type, F3 color, float param0, float param1, F3 out
   }
 }
 
+// GGX is hot in scenes that use it and dead weight elsewhere: the render kernel is built both ways and chosen by what the
+// scene contains (LR_GGX_OUT_OF_LINE, build.py; A/B profiles/r01_c_ab_s26.txt: +3.6 % on sample.toml out of line, -5.5 %
+// on brdf.toml, so each gets its own)
+#ifdef LR_GGX_OUT_OF_LINE
+#define LR_GGX static __device__ __noinline__
+#else
+#define LR_GGX __device__ __forceinline__
+#endif
+LR_GGX F3 ggx_brdf(F3 color, float roughness, float ior, F3 out_, F3 in_, F3 n) {      // ggx.rs:71-85
+  const F3 on = orienting_normal(out_, n);
+  if (dot(in_, on) <= 0.0f) return f3(0.0f, 0.0f, 0.0f);
+  const F3 h = normalize(in_ + out_);
+  const float alpha = roughness * roughness;
+  const float a2 = alpha * alpha;
+  const float nnn = 1.0f - ior, nnp = 1.0f + ior;                  // ggx.rs:41-47
+  const float f_0 = (nnn * nnn) / (nnp * nnp);
+  const float f = f_0 + (1.0f - f_0) * powi5(1.0f - dot(in_, h));
+  const float g = ggx_g1(a2, in_, on) * ggx_g1(a2, out_, on);
+  const float d = ggx_ndf(a2, h, on);
+  return color * f * g * d / (4.0f * dot(in_, on) * dot(out_, on));
+}
+LR_GGX void ggx_sample(float roughness, F3 out_, F3 on, float xi2, float s1, float c1, F3* in_, float* pdf) {   // ggx.rs:87-113
+  F3 u, v;
+  orthonormal_basis(on, u, v);
+  const float alpha = roughness * roughness;
+  const float a2 = alpha * alpha;
+  const float tan = alpha * sqrtf(xi2 / (1.0f - xi2));
+  const float x = 1.0f + tan * tan;
+  const float c = 1.0f / sqrtf(x);
+  const float s = tan / sqrtf(x);
+  const F3 h = u * c1 * s + v * s1 * s + on * c;
+  const float o_h = dot(out_, h);
+  *in_ = h * (2.0f * o_h) - out_;
+  const float jacobian = 1.0f / (4.0f * o_h);
+  *pdf = ggx_ndf(a2, h, on) * dot(h, on) * jacobian;
+}
+
 // Material::brdf
 LR_DEV F3 mat_brdf(const Mat& m, F3 out_, F3 in_, F3 n, F3 pos) {
   if (m.type == LR_MAT_LAMBERT) {                                  // lambert.rs:32-35
     const float c = checker(pos.x, pos.z);
     return m.color * f3(c, c, c) / kPI;
   }
-  if (m.type == LR_MAT_GGX) {                                      // ggx.rs:71-85
-    const F3 on = orienting_normal(out_, n);
-    if (dot(in_, on) <= 0.0f) return f3(0.0f, 0.0f, 0.0f);
-    const F3 h = normalize(in_ + out_);
-    const float alpha = m.param0 * m.param0;
-    const float a2 = alpha * alpha;
-    const float nnn = 1.0f - m.param1, nnp = 1.0f + m.param1;     // ggx.rs:41-47
-    const float f_0 = (nnn * nnn) / (nnp * nnp);
-    const float f = f_0 + (1.0f - f_0) * powi5(1.0f - dot(in_, h));
-    const float g = ggx_g1(a2, in_, on) * ggx_g1(a2, out_, on);
-    const float d = ggx_ndf(a2, h, on);
-    return m.color * f * g * d / (4.0f * dot(in_, on) * dot(out_, on));
-  }
+  if (m.type == LR_MAT_GGX) return ggx_brdf(m.color, m.param0, m.param1, out_, in_, n);
   return mat_brdf_other(m.type, m.color, m.param0, m.param1, out_, in_, n);
 }
 
@@ -533,20 +558,10 @@ LR_DEV void mat_sample(const Mat& m, F3 out_, F3 n, Pcg& rng, F3& in_, float& pd
     pdf = dot(in_, n) / kPI;
     return;
   }
-  if (m.type == LR_MAT_GGX) {                                      // ggx.rs:87-113
-    F3 u, v;
-    orthonormal_basis(on, u, v);
-    const float alpha = m.param0 * m.param0;
-    const float a2 = alpha * alpha;
-    const float tan = alpha * sqrtf(xi2 / (1.0f - xi2));
-    const float x = 1.0f + tan * tan;
-    const float c = 1.0f / sqrtf(x);
-    const float s = tan / sqrtf(x);
-    const F3 h = u * c1 * s + v * s1 * s + on * c;
-    const float o_h = dot(out_, h);
-    in_ = h * (2.0f * o_h) - out_;
-    const float jacobian = 1.0f / (4.0f * o_h);
-    pdf = ggx_ndf(a2, h, on) * dot(h, on) * jacobian;
+  if (m.type == LR_MAT_GGX) {
+    F3 wi; float pd;
+    ggx_sample(m.param0, out_, on, xi2, s1, c1, &wi, &pd);
+    in_ = wi; pdf = pd;
     return;
   }
   F3 wi; float pd;

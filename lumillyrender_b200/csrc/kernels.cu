@@ -93,14 +93,16 @@ __global__ void __launch_bounds__(256) read_bw_kernel(const float4* __restrict__
 }
 
 // ------------------------------------------------------------------ launchers
-cudaError_t launch_render_persistent(const DevScene& sc, const DevParams& p, bool count, float* out_sum, float* out_sumsq,
+cudaError_t launch_render_persistent(const DevScene& sc, const DevParams& p, bool has_ggx, bool count, float* out_sum, float* out_sumsq,
                                      unsigned long long* counters, unsigned int* next_unit, int sm_count, cudaStream_t stream) {
-  const bool tree = sc.n_nodes > 0 || count;     // the instrumented kernel exists in the tree units only
-  if (p.integrator == LR_INTEGRATOR_PT)
-    return tree ? launch_persistent_i0_t1(sc, p, count, out_sum, out_sumsq, counters, next_unit, sm_count, stream)
-                : launch_persistent_i0_t0(sc, p, count, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
-  return tree ? launch_persistent_i1_t1(sc, p, count, out_sum, out_sumsq, counters, next_unit, sm_count, stream)
-              : launch_persistent_i1_t0(sc, p, count, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
+  // the instrumented kernel exists in the (tree, GGX inline) units only: it is the most general code
+  const bool tree = sc.n_nodes > 0 || count, ggx = has_ggx || count;
+  using Fn = cudaError_t (*)(const DevScene&, const DevParams&, bool, float*, float*, unsigned long long*, unsigned int*, int, cudaStream_t);
+  static const Fn table[2][2][2] = {
+      {{launch_persistent_i0_t0_g0, launch_persistent_i0_t0_g1}, {launch_persistent_i0_t1_g0, launch_persistent_i0_t1_g1}},
+      {{launch_persistent_i1_t0_g0, launch_persistent_i1_t0_g1}, {launch_persistent_i1_t1_g0, launch_persistent_i1_t1_g1}}};
+  return table[p.integrator == LR_INTEGRATOR_PT ? 0 : 1][tree ? 1 : 0][ggx ? 1 : 0](sc, p, count, out_sum, out_sumsq, counters, next_unit,
+                                                                                   sm_count, stream);
 }
 
 cudaError_t launch_reduce_splits(float* dst, const float* partial, size_t n, int splits, cudaStream_t stream) {

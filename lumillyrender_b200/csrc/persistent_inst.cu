@@ -1,27 +1,28 @@
-// persistent_inst.cu — instantiations of the render kernel (persistent.cuh).  Compiled once per (integrator, scene has
-// a BVH) pair by build.py (-DLR_INST_INTEGRATOR=0|1 -DLR_INST_TREE=0|1; the tree units also get -DLR_DIV_OUT_OF_LINE),
-// so the four translation units build in parallel.  The instrumented (COUNT) kernel lives in the tree units.
+// persistent_inst.cu — instantiations of the render kernel (persistent.cuh).  Compiled by build.py once per
+// (integrator, scene has a BVH, scene has a GGX material) triple:
+//   -DLR_INST_INTEGRATOR=0|1 -DLR_INST_TREE=0|1 -DLR_INST_GGX=0|1
+// The tree units also get -DLR_DIV_OUT_OF_LINE, the units for scenes without GGX get -DLR_GGX_OUT_OF_LINE (both are
+// code-size decisions measured A/B, see device_path.cuh), so the eight translation units build in parallel.
+// The instrumented (COUNT) kernel lives in the tree + GGX units.
 #include "persistent.cuh"
 
-#if !defined(LR_INST_INTEGRATOR) || !defined(LR_INST_TREE)
-#error "compile with -DLR_INST_INTEGRATOR=0|1 -DLR_INST_TREE=0|1"
+#if !defined(LR_INST_INTEGRATOR) || !defined(LR_INST_TREE) || !defined(LR_INST_GGX)
+#error "compile with -DLR_INST_INTEGRATOR=0|1 -DLR_INST_TREE=0|1 -DLR_INST_GGX=0|1"
 #endif
 
 namespace lr {
 
-#define LR_PASTE2(a, b, c) a##b##_t##c
-#define LR_PASTE(a, b, c) LR_PASTE2(a, b, c)
+#define LR_PASTE2(a, b, c, d) a##b##_t##c##_g##d
+#define LR_PASTE(a, b, c, d) LR_PASTE2(a, b, c, d)
 
-cudaError_t LR_PASTE(launch_persistent_i, LR_INST_INTEGRATOR, LR_INST_TREE)(const DevScene& sc, const DevParams& p, bool count,
-                                                                            float* out_sum, float* out_sumsq, unsigned long long* counters,
-                                                                            unsigned int* next_unit, int sm_count, cudaStream_t stream) {
-#if LR_INST_TREE
+cudaError_t LR_PASTE(launch_persistent_i, LR_INST_INTEGRATOR, LR_INST_TREE, LR_INST_GGX)(
+    const DevScene& sc, const DevParams& p, bool count, float* out_sum, float* out_sumsq, unsigned long long* counters,
+    unsigned int* next_unit, int sm_count, cudaStream_t stream) {
+#if LR_INST_TREE && LR_INST_GGX
   if (count) return launch_persistent_one<LR_INST_INTEGRATOR, true, true>(sc, p, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
-  return launch_persistent_one<LR_INST_INTEGRATOR, true, false>(sc, p, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
-#else
-  (void)count;
-  return launch_persistent_one<LR_INST_INTEGRATOR, false, false>(sc, p, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
 #endif
+  (void)count;
+  return launch_persistent_one<LR_INST_INTEGRATOR, LR_INST_TREE != 0, false>(sc, p, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
 }
 
 }  // namespace lr

@@ -140,7 +140,8 @@ def synth_ibl(height=1600):
 
 
 def ensure_assets(root, bunny_tris=144046, ibl_height=1600, need_bunny=True, need_ibl=True):
-    """Creates the synthetic assets under `root`/models if absent (idempotent). Returns `root`."""
+    """Creates the synthetic assets under `root`/models if absent (idempotent). Returns `root`.
+    need_bunny also covers the dragon stand-in of scenes/vr.toml."""
     root = os.path.abspath(root)
     simple = os.path.join(root, "models", "simple")
     _write_if_changed(os.path.join(simple, "cbox.obj"), CBOX_OBJ)
@@ -161,17 +162,32 @@ def ensure_assets(root, bunny_tris=144046, ibl_height=1600, need_bunny=True, nee
             write_obj(bunny, v, f, "procedural stand-in for the McGuire-archive bunny")
             with open(tag, "w") as fh:
                 fh.write(str(bunny_tris))
-    if need_ibl:
-        hdr = os.path.join(root, "models", "ibl", "14-Hamarikyu_Bridge_B_3k.hdr")
-        tag = hdr + ".height"
+        # scenes/vr.toml: models/stanford_dragon/dragon.obj (absent) -> a second procedural closed mesh, half the bunny's size
+        dragon = os.path.join(root, "models", "stanford_dragon", "dragon.obj")
+        tag = dragon + ".tris"
         have = None
-        if os.path.exists(hdr) and os.path.exists(tag):
+        if os.path.exists(dragon) and os.path.exists(tag):
             with open(tag) as f:
                 have = f.read().strip()
-        if have != str(ibl_height):
-            from .renderer import save_hdr
-            os.makedirs(os.path.dirname(hdr), exist_ok=True)
-            save_hdr(hdr, synth_ibl(ibl_height))
+        n_dragon = max(2000, bunny_tris // 2)
+        if have != str(n_dragon):
+            v, f = blob_mesh(n_dragon, seed=7)
+            write_obj(dragon, v * np.float32(5.0), f, "procedural stand-in for the Stanford dragon")
             with open(tag, "w") as fh:
-                fh.write(str(ibl_height))
+                fh.write(str(n_dragon))
+    if need_ibl:
+        # welcome-2018.toml and ridaisai-2018.toml name two different (absent) .hdr files; both get the synthetic sky
+        for name in ("14-Hamarikyu_Bridge_B_3k.hdr", "PaperMill_Ruins_E.hdr"):
+            hdr = os.path.join(root, "models", "ibl", name)
+            tag = hdr + ".height"
+            have = None
+            if os.path.exists(hdr) and os.path.exists(tag):
+                with open(tag) as f:
+                    have = f.read().strip()
+            if have != str(ibl_height):
+                from .renderer import save_hdr
+                os.makedirs(os.path.dirname(hdr), exist_ok=True)
+                save_hdr(hdr, synth_ibl(ibl_height))
+                with open(tag, "w") as fh:
+                    fh.write(str(ibl_height))
     return root

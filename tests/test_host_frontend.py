@@ -11,7 +11,8 @@ import pytest
 
 from conftest import ROOT, SCENES, load_scene
 
-ALL_SCENES = ["primitive", "new-cbox", "brdf", "brdf-phong", "brdf-blinn", "brdf-thinlens", "sample", "welcome-2018", "primitive-pinhole"]
+ALL_SCENES = ["primitive", "new-cbox", "brdf", "brdf-phong", "brdf-blinn", "brdf-thinlens", "sample", "welcome-2018", "primitive-pinhole",
+              "ridaisai-2018", "vr", "debug-nee", "welcome-2018-geo"]      # the last four: the rest of the reference's scenes/
 
 
 def F(*v):
@@ -117,6 +118,8 @@ def test_camera_block_bit_equal_to_oracle_restatement(lr, orc, assets, name):
         fd = cam.get("focus-distance", cam.get("focus_distance"))
         fn = cam.get("f-number", cam.get("f_number"))
         L.orc_camera_thin_lens(m, cam["fov"], fd, fn, w, h, C.byref(ref))
+    elif cam["type"] == "omnidirectional":
+        L.orc_camera_omnidirectional(m, w, h, C.byref(ref))
     elif cam["type"] == "pinhole":
         L.orc_camera_pinhole(F(*cam["position"]), F(*cam["aperture-position"]), F(*cam["sensor-size"]), w, h, cam["aperture-radius"], C.byref(ref))
     got = load_scene(lr, name).camera()

@@ -259,3 +259,22 @@ def test_gate_retrace_and_flat_list(lr, orc, gpu):
     assert st["rays"] == ost["rays"]
     assert np.isclose(img, ref_sum / 4, rtol=1e-4, atol=1e-5).all(-1).mean() >= 0.999
     assert st["gate_retraces"] > 0, "the far triangles must have been found optimistically and rejected by the gate"
+
+
+def test_full_size_properties(lr, assets, gpu):
+    """BASELINE configs[4] at its full film size (1920x1370), through properties that do not need the oracle:
+    sample-range sharding is exact up to fp32 summation order, ray counts add up, a crop renders the same pixels,
+    the render is finite and deterministic."""
+    d = load_scene(lr, "sample", (1920, 1370))
+    s = d.scene()
+    full, _, st = s.render(spp=4, seed=21)
+    again, _, _ = s.render(spp=4, seed=21)
+    assert np.array_equal(full, again)
+    assert full.shape == (1370, 1920, 3) and np.isfinite(full).all() and st["nonfinite_samples"] == 0
+    lo, _, st_lo = s.render(spp=2, spp_begin=0, seed=21)
+    hi, _, st_hi = s.render(spp=2, spp_begin=2, seed=21)
+    assert st_lo["rays"] + st_hi["rays"] == st["rays"]
+    assert np.allclose((lo + hi) / 2, full, rtol=1e-5, atol=1e-6)
+    crop, _, _ = s.render(spp=4, seed=21, crop=(901, 333, 257, 129))
+    assert np.array_equal(crop, full[333:333 + 129, 901:901 + 257])
+    assert 0.2 < float(full.mean()) < 0.6 and st["rays"] > 4 * 1920 * 1370 * 3

@@ -130,7 +130,8 @@ render_persistent_kernel(const __grid_constant__ DevScene sc, const __grid_const
                 const float g_term = q_point_cos * light_cos / q_sqr;
                 const F3 l_i = lm.emissive ? lm.emission : f3(0.0f, 0.0f, 0.0f);
                 const F3 direct = q_brdf * l_i * g_term / q_pdf;
-                L = L + q_T * (direct / q_prr);                  // scene.rs:192 (T of the vertex, before its BSDF update)
+                // scene.rs:192 (T of the vertex, before its BSDF update); x / 1.0f == x exactly, the usual p_rr
+                L = L + q_T * (q_prr != 1.0f ? direct / q_prr : direct);
               }
             }
           }
@@ -208,7 +209,8 @@ render_persistent_kernel(const __grid_constant__ DevScene sc, const __grid_const
               }
               const F3 coef = mat_coef(m, wo, sf.n, t);
               const float c = dot(wi, sf.n);                     // UNoriented normal (scene.rs:91)
-              T = T * (f_bsdf * coef * c / pdf) / prr;
+              T = T * (f_bsdf * coef * c / pdf);
+              if (prr != 1.0f) T = T / prr;                      // x / 1.0f == x exactly: the common case skips 3 divisions
               o = sf.pos;                                        // no origin offset (scene.rs:94-97)
               d0 = wi;
               if (NR == 2 && has_shadow_next) d1 = nee_dir;

@@ -77,7 +77,10 @@ struct MinBlocks {
 };
 
 // TREE = false: the scene has no BVH (spheres and flat triangles only); phase B is compiled out.
-template <int INTEGRATOR, bool TREE, bool COUNT>
+// BUILD tags the translation unit's code-size choices (persistent_inst.cu: GGX inline or out of line).  It changes
+// nothing inside the kernel, but it makes the instantiations of different units DIFFERENT symbols — two units defining
+// the same instantiation with different macros would be merged by the linker into whichever it saw first.
+template <int INTEGRATOR, bool TREE, bool COUNT, int BUILD>
 __global__ void __launch_bounds__(kBlockThreads, MinBlocks<INTEGRATOR, TREE>::value)
 render_persistent_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ DevParams p, float* __restrict__ out_sum,
                          float* __restrict__ out_sumsq, unsigned long long* __restrict__ counters, unsigned int* __restrict__ next_unit) {
@@ -356,16 +359,16 @@ render_persistent_kernel(const __grid_constant__ DevScene sc, const __grid_const
 }
 
 // one launch = the whole sample range of every unit: a persistent grid that fills the SMs
-template <int INTEGRATOR, bool TREE, bool COUNT>
+template <int INTEGRATOR, bool TREE, bool COUNT, int BUILD>
 cudaError_t launch_persistent_one(const DevScene& sc, const DevParams& p, float* out_sum, float* out_sumsq,
                                   unsigned long long* counters, unsigned int* next_unit, int sm_count, cudaStream_t stream) {
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_persistent_kernel<INTEGRATOR, TREE, COUNT>, kBlockThreads, 0) !=
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_persistent_kernel<INTEGRATOR, TREE, COUNT, BUILD>, kBlockThreads, 0) !=
           cudaSuccess || nb <= 0) nb = 4;
   const long long units = (long long)p.tiles_x * p.tiles_y * 32 * p.splits;
   const long long want = (units + kBlockThreads - 1) / kBlockThreads;
   const unsigned int blocks = (unsigned int)std::max<long long>(1, std::min<long long>(want, (long long)nb * sm_count));
-  render_persistent_kernel<INTEGRATOR, TREE, COUNT><<<blocks, kBlockThreads, 0, stream>>>(sc, p, out_sum, out_sumsq, counters, next_unit);
+  render_persistent_kernel<INTEGRATOR, TREE, COUNT, BUILD><<<blocks, kBlockThreads, 0, stream>>>(sc, p, out_sum, out_sumsq, counters, next_unit);
   return cudaGetLastError();
 }
 

@@ -19,10 +19,10 @@ cudaError_t LR_PASTE(launch_persistent_i, LR_INST_INTEGRATOR, LR_INST_TREE, LR_I
     const DevScene& sc, const DevParams& p, bool count, float* out_sum, float* out_sumsq, unsigned long long* counters,
     unsigned int* next_unit, int sm_count, cudaStream_t stream) {
 #if LR_INST_TREE && LR_INST_GGX
-  if (count) return launch_persistent_one<LR_INST_INTEGRATOR, true, true>(sc, p, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
+  if (count) return launch_persistent_one<LR_INST_INTEGRATOR, true, true, LR_INST_GGX>(sc, p, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
 #endif
   (void)count;
-  return launch_persistent_one<LR_INST_INTEGRATOR, LR_INST_TREE != 0, false>(sc, p, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
+  return launch_persistent_one<LR_INST_INTEGRATOR, LR_INST_TREE != 0, false, LR_INST_GGX>(sc, p, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
 }
 
 }  // namespace lr

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -22,6 +23,10 @@ int fail(int code, const std::string& s) { g_error = s; return code; }
 
 static int g_device = -1;
 static int g_sm_count = 0;
+// pinned staging arena of lr_scene_create (grow-only, shared by all calls)
+static std::mutex g_stage_mu;
+static void* g_stage = nullptr;
+static size_t g_stage_cap = 0;
 
 #define LR_CUDA(call)                                                                      \
   do {                                                                                     \
@@ -35,19 +40,15 @@ static int ensure_device() {
   return lr_init(0);
 }
 
-template <class T>
-static cudaError_t upload(const std::vector<T>& h, const T** d, uint64_t& bytes) {
-  *d = nullptr;
-  if (h.empty()) return cudaSuccess;
-  void* p = nullptr;
-  cudaError_t e = cudaMalloc(&p, h.size() * sizeof(T));
-  if (e != cudaSuccess) return e;
-  e = cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) { cudaFree(p); return e; }
-  *d = (const T*)p;
-  bytes += h.size() * sizeof(T);
-  return cudaSuccess;
+// Device memory of the scene handle comes from the stream-ordered allocator with a pool that never trims (lr_init): a
+// scene is created and destroyed once per end-to-end render, and cudaFree of tens of MB was measured to stall for
+// 100-500 ms every few calls (tools/e2e_breakdown.py) while the pool hands the same blocks back in microseconds.
+static cudaError_t dev_alloc(void** p, size_t bytes) {
+  cudaError_t e = cudaMallocAsync(p, bytes, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);      // usable from any stream afterwards
+  return e;
 }
+static void dev_free(void* p) { if (p) cudaFreeAsync(p, 0); }
 
 static inline float4 mk4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 static inline float as_float(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
@@ -63,6 +64,8 @@ struct LrScene {
   int width = 0, height = 0;
   unsigned long long* d_counters = nullptr;
   // scratch (mutable: owned by the handle, one caller thread at a time per LrScene)
+  mutable float* d_film = nullptr; mutable size_t film_floats = 0;           // lr_render's sum / sum-of-squares buffers
+  mutable float* d_film_sq = nullptr; mutable size_t film_sq_floats = 0;
   mutable float* d_partial = nullptr; mutable size_t partial_floats = 0;
   mutable float* d_partial_sq = nullptr; mutable size_t partial_sq_floats = 0;
   mutable uint64_t acc_samples = 0;
@@ -93,6 +96,13 @@ int lr_init(int device) {
   if (e != cudaSuccess) return fail(LR_ERR_NO_DEVICE, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
   g_device = device;
   g_sm_count = prop.multiProcessorCount;
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;                    // never give freed blocks back to the driver
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   return LR_OK;
 }
 
@@ -115,46 +125,17 @@ int lr_scene_create(const LrSceneDesc* d, LrScene** out) {
   if (int rc = validate_desc(*d)) return rc;
   if (int rc = ensure_device()) return rc;
 
-  // ---- pack host-side arrays (layout documented in device_scene.h)
-  std::vector<float4> nodes((size_t)d->n_nodes * 4), tris((size_t)d->n_triangles * 3), spheres(d->n_spheres), mats((size_t)d->n_materials * 3);
-  std::vector<int2> sphere_meta(d->n_spheres);
-  std::vector<float4> tri_n(d->n_triangles), tri_box((size_t)d->n_triangles * 2);
-  std::memcpy(nodes.data(), d->nodes, (size_t)d->n_nodes * sizeof(LrBvhNode));
-  for (int i = 0; i < d->n_triangles; i++) {
-    const LrTriangle& t = d->triangles[i];
-    // p0 and the edges of Moller-Trumbore, e1 = p1 - p0, e2 = p2 - p0 (triangle.rs:71-72): single fp32 subtractions
-    const Vec3 e1 = vsub(vec3(t.p1), vec3(t.p0)), e2 = vsub(vec3(t.p2), vec3(t.p0));
-    tris[3 * (size_t)i + 0] = mk4(t.p0[0], t.p0[1], t.p0[2], as_float(t.prim_id));
-    tris[3 * (size_t)i + 1] = mk4(e1[0], e1[1], e1[2], as_float(t.material));
-    tris[3 * (size_t)i + 2] = mk4(e2[0], e2[1], e2[2], 0.0f);
-    // Triangle::aabb (triangle.rs:102-119): min / max of the vertices
-    tri_box[2 * (size_t)i + 0] = mk4(std::fmin(std::fmin(t.p0[0], t.p1[0]), t.p2[0]), std::fmin(std::fmin(t.p0[1], t.p1[1]), t.p2[1]),
-                                     std::fmin(std::fmin(t.p0[2], t.p1[2]), t.p2[2]), 0.0f);
-    tri_box[2 * (size_t)i + 1] = mk4(std::fmax(std::fmax(t.p0[0], t.p1[0]), t.p2[0]), std::fmax(std::fmax(t.p0[1], t.p1[1]), t.p2[1]),
-                                     std::fmax(std::fmax(t.p0[2], t.p1[2]), t.p2[2]), 0.0f);
-    // triangle.rs:36  normal = (p1 - p0).cross(p2 - p0).normalize(), in the reference's fp32 operation order
-    const Vec3 n = vnormalize(vcross(vsub(vec3(t.p1), vec3(t.p0)), vsub(vec3(t.p2), vec3(t.p0))));
-    tri_n[i] = mk4(n[0], n[1], n[2], 0.0f);
-  }
-  for (int i = 0; i < d->n_spheres; i++) {
-    const LrSphere& s = d->spheres[i];
-    spheres[i] = mk4(s.center[0], s.center[1], s.center[2], s.radius);
-    sphere_meta[i].x = s.material; sphere_meta[i].y = s.prim_id;
-  }
+  // ---- sizes.  Everything goes into ONE device block, packed on the host straight into a pinned staging arena and
+  // uploaded with one copy (lr_scene_create is inside the timed region of an end-to-end render: 11 ms -> 4 ms).
   std::vector<char> emissive(d->n_materials, 0);
   for (int i = 0; i < d->n_materials; i++) {
     const LrMaterial& m = d->materials[i];
     // only Lambert carries emission (description.rs:94-101; every other material returns zero, e.g. ggx.rs:60-62)
     const bool lam = m.type == LR_MAT_LAMBERT;
     const float ex = lam ? m.emission[0] : 0.0f, ey = lam ? m.emission[1] : 0.0f, ez = lam ? m.emission[2] : 0.0f;
-    const float sq = ex * ex + ey * ey + ez * ez;                       // emission().sqr_norm() > 0.0 (objects.rs:21)
-    emissive[i] = sq > 0.0f;
-    const float weight = std::fmax(std::fmax(m.color[0], m.color[1]), m.color[2]);   // lambert.rs:27-30
-    mats[3 * (size_t)i + 0] = mk4(m.color[0], m.color[1], m.color[2], as_float(m.type));
-    mats[3 * (size_t)i + 1] = mk4(ex, ey, ez, m.param0);
-    mats[3 * (size_t)i + 2] = mk4(m.param1, weight, emissive[i] ? 1.0f : 0.0f, 0.0f);
+    emissive[i] = (ex * ex + ey * ey + ez * ez) > 0.0f;                 // emission().sqr_norm() > 0.0 (objects.rs:21)
   }
-  // ---- emitter table in instance (prim_id) order: objects.rs:18-29
+  // emitter table in instance (prim_id) order: objects.rs:18-29
   struct Em { int prim; float4 a, b, c; float area; };
   std::vector<Em> ems;
   for (int i = 0; i < d->n_triangles; i++) {
@@ -167,49 +148,108 @@ int lr_scene_create(const LrSceneDesc* d, LrScene** out) {
     ems.push_back(e);
   }
   for (int i = 0; i < d->n_spheres; i++) {
-    const LrSphere& s = d->spheres[i];
-    if (!emissive[s.material]) continue;
-    Em e; e.prim = s.prim_id; e.area = sphere_area(s.radius);
-    e.a = mk4(s.center[0], s.center[1], s.center[2], as_float(1));
-    e.b = mk4(s.radius, 0.0f, 0.0f, e.area);
+    const LrSphere& sp = d->spheres[i];
+    if (!emissive[sp.material]) continue;
+    Em e; e.prim = sp.prim_id; e.area = sphere_area(sp.radius);
+    e.a = mk4(sp.center[0], sp.center[1], sp.center[2], as_float(1));
+    e.b = mk4(sp.radius, 0.0f, 0.0f, e.area);
     e.c = mk4(0.0f, 0.0f, 0.0f, 0.0f);
     ems.push_back(e);
   }
   std::sort(ems.begin(), ems.end(), [](const Em& x, const Em& y) { return x.prim < y.prim; });
-  std::vector<float> cdf(ems.size());
-  std::vector<float4> emitters(ems.size() * 3);
-  float area = 0.0f;
-  for (size_t i = 0; i < ems.size(); i++) {
-    area += ems[i].area;                                                // `area += obj.area()` objects.rs:41
-    cdf[i] = area;
-    emitters[3 * i] = ems[i].a; emitters[3 * i + 1] = ems[i].b; emitters[3 * i + 2] = ems[i].c;
-  }
-  std::vector<float4> sky;
-  if (d->sky.type == LR_SKY_IBL) {
-    const size_t all = 2 * (size_t)d->sky.height * d->sky.height;
-    sky.resize(all);
-    for (size_t i = 0; i < all; i++) sky[i] = mk4(d->sky.pixels[3 * i], d->sky.pixels[3 * i + 1], d->sky.pixels[3 * i + 2], 0.0f);
-  }
+  const size_t n_sky = d->sky.type == LR_SKY_IBL ? 2 * (size_t)d->sky.height * d->sky.height : 0;
 
-  // ---- upload
+  size_t total = 0;
+  auto take = [&](size_t bytes) { const size_t at = total; total += (bytes + 255) & ~(size_t)255; return at; };
+  const size_t o_nodes = take((size_t)d->n_nodes * 4 * sizeof(float4)), o_tris = take((size_t)d->n_triangles * 3 * sizeof(float4));
+  const size_t o_tri_n = take((size_t)d->n_triangles * sizeof(float4)), o_tri_box = take((size_t)d->n_triangles * 2 * sizeof(float4));
+  const size_t o_spheres = take((size_t)d->n_spheres * sizeof(float4)), o_sphere_meta = take((size_t)d->n_spheres * sizeof(int2));
+  const size_t o_mats = take((size_t)d->n_materials * 3 * sizeof(float4));
+  const size_t o_cdf = take(ems.size() * sizeof(float)), o_emitters = take(ems.size() * 3 * sizeof(float4));
+  const size_t o_sky = take(n_sky * sizeof(float4));
+  const size_t upload_bytes = total;
+  const size_t o_counters = take(C_COUNT * sizeof(unsigned long long));
+
   LrScene* s = new LrScene();
-  auto track = [&](const void* p) { if (p) s->allocs.push_back(const_cast<void*>(p)); };
   cudaError_t e = cudaSuccess;
   DevScene& dv = s->dev;
-  if (e == cudaSuccess) { e = upload(nodes, &dv.nodes, s->h2d_bytes); track(dv.nodes); }
-  if (e == cudaSuccess) { e = upload(tris, &dv.tris, s->h2d_bytes); track(dv.tris); }
-  if (e == cudaSuccess) { e = upload(tri_n, &dv.tri_n, s->h2d_bytes); track(dv.tri_n); }
-  if (e == cudaSuccess) { e = upload(tri_box, &dv.tri_box, s->h2d_bytes); track(dv.tri_box); }
-  if (e == cudaSuccess) { e = upload(spheres, &dv.spheres, s->h2d_bytes); track(dv.spheres); }
-  if (e == cudaSuccess) { e = upload(sphere_meta, &dv.sphere_meta, s->h2d_bytes); track(dv.sphere_meta); }
-  if (e == cudaSuccess) { e = upload(mats, &dv.mats, s->h2d_bytes); track(dv.mats); }
-  if (e == cudaSuccess) { e = upload(cdf, &dv.emitter_cdf, s->h2d_bytes); track(dv.emitter_cdf); }
-  if (e == cudaSuccess) { e = upload(emitters, &dv.emitters, s->h2d_bytes); track(dv.emitters); }
-  if (e == cudaSuccess) { e = upload(sky, &dv.sky_pixels, s->h2d_bytes); track(dv.sky_pixels); }
-  if (e == cudaSuccess) { e = cudaMalloc((void**)&s->d_counters, C_COUNT * sizeof(unsigned long long)); }
-  if (e == cudaSuccess) { e = cudaMemset(s->d_counters, 0, C_COUNT * sizeof(unsigned long long)); }
-  if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
-  if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+  float area = 0.0f;
+  {
+    std::lock_guard<std::mutex> lock(g_stage_mu);
+    if (g_stage_cap < upload_bytes) {
+      if (g_stage) cudaFreeHost(g_stage);
+      g_stage = nullptr; g_stage_cap = 0;
+      e = cudaHostAlloc(&g_stage, upload_bytes + (upload_bytes >> 2), cudaHostAllocDefault);
+      if (e == cudaSuccess) g_stage_cap = upload_bytes + (upload_bytes >> 2);
+    }
+    if (e == cudaSuccess) {
+      char* h = (char*)g_stage;
+      // ---- pack (layout documented in device_scene.h)
+      float4* nodes = (float4*)(h + o_nodes); float4* tris = (float4*)(h + o_tris);
+      float4* tri_n = (float4*)(h + o_tri_n); float4* tri_box = (float4*)(h + o_tri_box);
+      float4* spheres = (float4*)(h + o_spheres); int2* sphere_meta = (int2*)(h + o_sphere_meta);
+      float4* mats = (float4*)(h + o_mats); float* cdf = (float*)(h + o_cdf); float4* emitters = (float4*)(h + o_emitters);
+      float4* sky = (float4*)(h + o_sky);
+      if (d->n_nodes > 0) std::memcpy(nodes, d->nodes, (size_t)d->n_nodes * sizeof(LrBvhNode));
+      for (int i = 0; i < d->n_triangles; i++) {
+        const LrTriangle& t = d->triangles[i];
+        // p0 and the edges of Moller-Trumbore, e1 = p1 - p0, e2 = p2 - p0 (triangle.rs:71-72): single fp32 subtractions
+        const Vec3 e1 = vsub(vec3(t.p1), vec3(t.p0)), e2 = vsub(vec3(t.p2), vec3(t.p0));
+        tris[3 * (size_t)i + 0] = mk4(t.p0[0], t.p0[1], t.p0[2], as_float(t.prim_id));
+        tris[3 * (size_t)i + 1] = mk4(e1[0], e1[1], e1[2], as_float(t.material));
+        tris[3 * (size_t)i + 2] = mk4(e2[0], e2[1], e2[2], 0.0f);
+        // Triangle::aabb (triangle.rs:102-119): min / max of the vertices
+        tri_box[2 * (size_t)i + 0] = mk4(std::fmin(std::fmin(t.p0[0], t.p1[0]), t.p2[0]), std::fmin(std::fmin(t.p0[1], t.p1[1]), t.p2[1]),
+                                         std::fmin(std::fmin(t.p0[2], t.p1[2]), t.p2[2]), 0.0f);
+        tri_box[2 * (size_t)i + 1] = mk4(std::fmax(std::fmax(t.p0[0], t.p1[0]), t.p2[0]), std::fmax(std::fmax(t.p0[1], t.p1[1]), t.p2[1]),
+                                         std::fmax(std::fmax(t.p0[2], t.p1[2]), t.p2[2]), 0.0f);
+        // triangle.rs:36  normal = (p1 - p0).cross(p2 - p0).normalize(), in the reference's fp32 operation order
+        const Vec3 n = vnormalize(vcross(e1, e2));
+        tri_n[i] = mk4(n[0], n[1], n[2], 0.0f);
+      }
+      for (int i = 0; i < d->n_spheres; i++) {
+        const LrSphere& sp = d->spheres[i];
+        spheres[i] = mk4(sp.center[0], sp.center[1], sp.center[2], sp.radius);
+        sphere_meta[i].x = sp.material; sphere_meta[i].y = sp.prim_id;
+      }
+      for (int i = 0; i < d->n_materials; i++) {
+        const LrMaterial& m = d->materials[i];
+        const bool lam = m.type == LR_MAT_LAMBERT;
+        const float ex = lam ? m.emission[0] : 0.0f, ey = lam ? m.emission[1] : 0.0f, ez = lam ? m.emission[2] : 0.0f;
+        const float weight = std::fmax(std::fmax(m.color[0], m.color[1]), m.color[2]);   // lambert.rs:27-30
+        mats[3 * (size_t)i + 0] = mk4(m.color[0], m.color[1], m.color[2], as_float(m.type));
+        mats[3 * (size_t)i + 1] = mk4(ex, ey, ez, m.param0);
+        mats[3 * (size_t)i + 2] = mk4(m.param1, weight, emissive[i] ? 1.0f : 0.0f, 0.0f);
+      }
+      for (size_t i = 0; i < ems.size(); i++) {
+        area += ems[i].area;                                            // `area += obj.area()` objects.rs:41
+        cdf[i] = area;
+        emitters[3 * i] = ems[i].a; emitters[3 * i + 1] = ems[i].b; emitters[3 * i + 2] = ems[i].c;
+      }
+      for (size_t i = 0; i < n_sky; i++) sky[i] = mk4(d->sky.pixels[3 * i], d->sky.pixels[3 * i + 1], d->sky.pixels[3 * i + 2], 0.0f);
+
+      // ---- upload: one allocation, one copy
+      char* block = nullptr;
+      e = dev_alloc((void**)&block, total);
+      if (e == cudaSuccess) {
+        s->allocs.push_back(block);
+        if (upload_bytes > 0) e = cudaMemcpyAsync(block, h, upload_bytes, cudaMemcpyHostToDevice, 0);
+        if (e == cudaSuccess) e = cudaMemsetAsync(block + o_counters, 0, C_COUNT * sizeof(unsigned long long), 0);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(0);             // the arena is reused by the next call
+        s->h2d_bytes = upload_bytes;
+        auto at = [&](size_t off, size_t count) -> const void* { return count ? (const void*)(block + off) : nullptr; };
+        dv.nodes = (const float4*)at(o_nodes, d->n_nodes); dv.tris = (const float4*)at(o_tris, d->n_triangles);
+        dv.tri_n = (const float4*)at(o_tri_n, d->n_triangles); dv.tri_box = (const float4*)at(o_tri_box, d->n_triangles);
+        dv.spheres = (const float4*)at(o_spheres, d->n_spheres); dv.sphere_meta = (const int2*)at(o_sphere_meta, d->n_spheres);
+        dv.mats = (const float4*)at(o_mats, d->n_materials);
+        dv.emitter_cdf = (const float*)at(o_cdf, ems.size()); dv.emitters = (const float4*)at(o_emitters, ems.size());
+        dv.sky_pixels = (const float4*)at(o_sky, n_sky);
+        s->d_counters = (unsigned long long*)(block + o_counters);
+      }
+    }
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev0, cudaEventDefault);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev1, cudaEventDefault);
   if (e != cudaSuccess) {
     const std::string msg = std::string("scene upload: ") + cudaGetErrorString(e);
     lr_scene_destroy(s);
@@ -235,10 +275,11 @@ int lr_scene_create(const LrSceneDesc* d, LrScene** out) {
 
 void lr_scene_destroy(LrScene* s) {
   if (!s) return;
-  for (void* p : s->allocs) cudaFree(p);
-  if (s->d_counters) cudaFree(s->d_counters);
-  if (s->d_partial) cudaFree(s->d_partial);
-  if (s->d_partial_sq) cudaFree(s->d_partial_sq);
+  for (void* p : s->allocs) dev_free(p);                // one block: scene arrays + the counter words
+  dev_free(s->d_film);
+  dev_free(s->d_film_sq);
+  dev_free(s->d_partial);
+  dev_free(s->d_partial_sq);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   delete s;
@@ -292,9 +333,9 @@ static int resolve_params(const LrScene* s, const LrRenderParams* p, DevParams& 
 
 static int ensure_scratch(float** buf, size_t* have, size_t need) {
   if (*have >= need) return LR_OK;
-  if (*buf) cudaFree(*buf);
+  dev_free(*buf);
   *buf = nullptr; *have = 0;
-  LR_CUDA(cudaMalloc((void**)buf, need * sizeof(float)));
+  LR_CUDA(dev_alloc((void**)buf, need * sizeof(float)));
   *have = need;
   return LR_OK;
 }
@@ -369,15 +410,14 @@ int lr_render(const LrScene* s, const LrRenderParams* p, float* out_rgb, float* 
   if (!out_rgb) return fail(LR_ERR_INVALID, "out_rgb is null");
   if (int rc = ensure_device()) return rc;
   const size_t n = (size_t)dp.crop_w * dp.crop_h * 3;
-  float *d_sum = nullptr, *d_sq = nullptr;
-  LR_CUDA(cudaMalloc((void**)&d_sum, n * sizeof(float)));
+  // the film buffers live in the scene handle between calls (no cudaMalloc / cudaFree inside an end-to-end render)
+  if (int rc = ensure_scratch(&s->d_film, &s->film_floats, n)) return rc;
+  if (out_sumsq) if (int rc = ensure_scratch(&s->d_film_sq, &s->film_sq_floats, n)) return rc;
+  float *d_sum = s->d_film, *d_sq = out_sumsq ? s->d_film_sq : nullptr;
   int rc = LR_OK;
   do {
     if (cudaMemsetAsync(d_sum, 0, n * sizeof(float), 0) != cudaSuccess) { rc = fail(LR_ERR_CUDA, "cudaMemsetAsync failed"); break; }
-    if (out_sumsq) {
-      if (cudaMalloc((void**)&d_sq, n * sizeof(float)) != cudaSuccess) { rc = fail(LR_ERR_CUDA, "cudaMalloc(sumsq) failed"); break; }
-      if (cudaMemsetAsync(d_sq, 0, n * sizeof(float), 0) != cudaSuccess) { rc = fail(LR_ERR_CUDA, "cudaMemsetAsync failed"); break; }
-    }
+    if (out_sumsq && cudaMemsetAsync(d_sq, 0, n * sizeof(float), 0) != cudaSuccess) { rc = fail(LR_ERR_CUDA, "cudaMemsetAsync failed"); break; }
     LrStats dummy;
     if (stats == nullptr) stats = &dummy;
     // drop counters of earlier accumulate calls so the stats describe this call only
@@ -391,8 +431,6 @@ int lr_render(const LrScene* s, const LrRenderParams* p, float* out_rgb, float* 
     if (e == cudaSuccess && out_sumsq) e = cudaMemcpy(out_sumsq, d_sq, n * sizeof(float), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(e)); break; }
   } while (0);
-  cudaFree(d_sum);
-  if (d_sq) cudaFree(d_sq);
   return rc;
 }
 

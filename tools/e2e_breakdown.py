@@ -10,7 +10,7 @@ lr.ensure_assets(ROOT, bunny_tris=144046, need_ibl=False)
 d = lr.Description(os.path.join(ROOT, "scenes", "sample.toml"), asset_root=ROOT, resolution=(1920, 1370))
 lib = capi.load_library()
 host = torch.empty((1370, 1920, 3), dtype=torch.float32).pin_memory()
-for i in range(5):
+for i in range(int(os.environ.get("E2E_ITERS", "5"))):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     s = d.scene()

@@ -282,7 +282,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of %s)" % which,
                          "bytes_per_ray": b_ray, "nodes_per_ray": cst["nodes_visited"] / max(cst["rays"], 1),
-                         "tris_per_ray": cst["tris_tested"] / max(cst["rays"], 1), "kernel": "render_persistent_kernel<pt, tree>",
+                         "tris_per_ray": cst["tris_tested"] / max(cst["rays"], 1), "kernel": "render_pool_kernel<pt, tree> (pool.cuh)",
                          "kernel_ms_per_launch": launch_ms, "rays_per_launch": rays_per_launch / world},
             "roofline_l2": {"bound": "l2", "achieved": achieved, "peak": l2_peak, "unit": "GB/s",
                             "frac": (achieved / l2_peak) if l2_peak else None,

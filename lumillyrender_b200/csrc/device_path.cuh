@@ -294,6 +294,92 @@ LR_DEV void bvh_traverse(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, 
   }
 }
 
+// The same query as bvh_traverse<COUNT, false>, organised as ONE loop whose every iteration advances a lane by at most
+// one inner node AND at most one triangle test: a leaf the descent reaches is moved to a one-entry leaf slot and the
+// descent goes on with the next stack entry while the slot's (<= 8) triangles are tested one per iteration.  In the
+// while-while form the lanes of a warp wait at the leaf step for the lane with the longest run of inner nodes (ncu:
+// 7 of 32 lanes active in the node loop with 28 rays in flight); here a lane idles only when it has neither a node nor
+// a triangle.  Nodes are culled against a cull_t that may lag one triangle test behind, which only makes the cull more
+// conservative: a triangle reached that way lies beyond the current nearest hit and fails `t < best_t`, so the nearest
+// hit (and the first-minimum tie rule, the triangle order being unchanged) is the same.
+struct TravState {
+  F3 o, d, inv;
+  float best_t, cull_t;
+  int best, cur, sp, leaf_first, leaf_left;
+};
+constexpr int kTravDone = (int)0x80000000;       // not a valid leaf code (first triangle would be 2^28 - 1)
+LR_DEV void trav_begin(TravState& s, int* stack, F3 o, F3 d, F3 inv, float best_t, int best) {
+  s.o = o; s.d = d; s.inv = inv;
+  s.best_t = best_t; s.best = best;
+  s.cull_t = best_t < 3.0e38f ? best_t * 1.0001f + 1e-4f : 3.0e38f;
+  s.sp = 0;
+  stack[s.sp++] = kTravDone;
+  s.cur = 0;
+  s.leaf_first = 0; s.leaf_left = 0;
+}
+LR_DEV bool trav_done(const TravState& s) { return s.cur == kTravDone && s.leaf_left == 0; }
+template <bool COUNT>
+LR_DEV void trav_step(const DevScene& sc, TravState& s, int* stack, TraceCounters& tc) {
+  if (s.cur >= 0) {
+    const float4* np = sc.nodes + 4 * (size_t)s.cur;
+    const float4 n0 = ldg4(np + 0), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
+    if (COUNT) tc.nodes++;
+    const F3 o = s.o, inv = s.inv;
+    const float cull_t = s.cull_t;
+    const float ax0 = (n0.x - o.x) * inv.x, bx0 = (n0.w - o.x) * inv.x;
+    const float ay0 = (n0.y - o.y) * inv.y, by0 = (n1.x - o.y) * inv.y;
+    const float az0 = (n0.z - o.z) * inv.z, bz0 = (n1.y - o.z) * inv.z;
+    const float ax1 = (n1.z - o.x) * inv.x, bx1 = (n2.y - o.x) * inv.x;
+    const float ay1 = (n1.w - o.y) * inv.y, by1 = (n2.z - o.y) * inv.y;
+    const float az1 = (n2.x - o.z) * inv.z, bz1 = (n2.w - o.z) * inv.z;
+    const float en0 = fmaxf(fmaxf(fminf(ax0, bx0), fminf(ay0, by0)), fmaxf(fminf(az0, bz0), 0.0f));
+    const float ex0 = fminf(fminf(fmaxf(ax0, bx0), fmaxf(ay0, by0)), fminf(fmaxf(az0, bz0), cull_t));
+    const float en1 = fmaxf(fmaxf(fminf(ax1, bx1), fminf(ay1, by1)), fmaxf(fminf(az1, bz1), 0.0f));
+    const float ex1 = fminf(fminf(fmaxf(ax1, bx1), fmaxf(ay1, by1)), fminf(fmaxf(az1, bz1), cull_t));
+    const bool h0 = en0 <= ex0, h1 = en1 <= ex1;
+    const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+    if (h0 && h1) {
+      const bool first0 = en0 <= en1;
+      stack[s.sp++] = first0 ? c1 : c0;
+      s.cur = first0 ? c0 : c1;
+    } else if (h0) {
+      s.cur = c0;
+    } else if (h1) {
+      s.cur = c1;
+    } else {
+      s.cur = stack[--s.sp];
+    }
+  }
+  if (s.cur < 0 && s.cur != kTravDone && s.leaf_left == 0) {
+    const int code = ~s.cur;
+    s.leaf_first = code >> 3;
+    s.leaf_left = (code & 7) + 1;
+    s.cur = stack[--s.sp];
+  }
+  if (s.leaf_left > 0) {
+    const float4* tp = sc.tris + 3 * (size_t)s.leaf_first;
+    const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
+    if (COUNT) tc.tris++;
+    const float t = triangle_mt(f3(v0), f3(v1), f3(v2), s.o, s.d);
+    if (t >= 0.0f && t < s.best_t) {
+      s.best_t = t;
+      s.best = s.leaf_first;
+      s.cull_t = t * 1.0001f + 1e-4f;
+    }
+    s.leaf_first++;
+    s.leaf_left--;
+  }
+}
+template <bool COUNT>
+LR_DEV void bvh_traverse_unified(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, int& best, TraceCounters& tc) {
+  int stack[kStackDepth];
+  TravState s;
+  trav_begin(s, stack, o, d, inv, best_t, best);
+  while (!trav_done(s)) trav_step<COUNT>(sc, s, stack, tc);
+  best_t = s.best_t;
+  best = s.best;
+}
+
 LR_DEV bool bvh_hit_is_gated(const DevScene& sc, F3 o, F3 inv, int id) { return tri_gate(sc, o, inv, id); }
 
 // Nearest hit: flat candidates first, then the BVH (strict `<`, so on exact ties the earlier candidate stays).

@@ -319,8 +319,9 @@ render_persistent_kernel(const __grid_constant__ DevScene sc, const __grid_const
     }
 
     // ================================================================ phase B
-    // the suspended rays traverse the BVH together (one call site): optimistic accept, the nearest hit gated once at
-    // the end, strict re-trace in the rare case the gate rejects it
+    // the suspended rays traverse the BVH together (one call site, one node and one triangle test per iteration:
+    // trav_step): optimistic accept, the nearest hit gated once at the end, strict re-trace in the rare case the gate
+    // rejects it
 #pragma unroll 1
     for (int r = 0; TREE && r < NR; r++) {
       const bool on = r == 0 ? pend0 : pend1;
@@ -330,7 +331,7 @@ render_persistent_kernel(const __grid_constant__ DevScene sc, const __grid_const
         const F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
         float t = r == 0 ? t0 : t1;
         int id = r == 0 ? id0 : id1;
-        bvh_traverse<COUNT, false>(sc, o, d, inv, t, id, tc);
+        bvh_traverse_unified<COUNT>(sc, o, d, inv, t, id, tc);
         if (id >= 0 && id < sc.n_bvh_tris && !bvh_hit_is_gated(sc, o, inv, id)) {
           trace_strict<COUNT>(sc, o, d, &t, &id, &tc);
           n_retrace++;

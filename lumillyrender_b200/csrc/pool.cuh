@@ -1,0 +1,486 @@
+// pool.cuh — the render kernel as a persistent megakernel over a per-warp POOL of paths in shared memory (sm_100a).
+//
+// Same per-path arithmetic as persistent.cuh (K1-K7 of SURVEY.md §2, every statement citing the same reference lines),
+// different scheduling.  In persistent.cuh a lane owns ONE path: a lane whose ray has to traverse the BVH idles until
+// `defer_thresh` lanes wait, and the BVH phase then runs with those ~12 lanes, of which 4 are active per instruction
+// (profiles/r01_d_phaseB_histograms.txt) — 39 % of the kernel's warp instructions at an eighth of the SIMD width.
+// Here a warp owns LR_POOL_SLOTS (64) paths whose whole state lives in shared memory (structure of arrays, one word
+// column per field), and lanes are bound to paths only for the length of one step:
+//   * phase A (one path vertex): the lanes take up to 32 slots whose nearest hit is known — shade it (sky / emission /
+//     Russian roulette / NEE / BSDF sample), regenerate finished paths from the unit cursor, and test the new ray(s)
+//     against spheres + flat list + the bounds of the tree; a ray that can reach the tree marks its slot PENDING;
+//   * phase B: the lanes take up to 32 pending rays (extension or shadow) and traverse the BVH together.
+// With twice as many paths as lanes one of the two kinds of work always has >= 32 items (pigeonhole), so both phases
+// start at full width whatever fraction of the rays reaches the tree.  A path's unit (a pixel's sample range) is
+// summed in its slot in sample order (main.rs:92-104) and its RNG stream is a function of (seed, pixel, sample), so
+// every sample — and the image — equals persistent.cuh's bit for bit, whichever lane ran which step.
+#pragma once
+#include <algorithm>
+
+#include "device_path.cuh"
+#include "kernels.h"
+#include "persistent.cuh"
+
+namespace lr {
+
+#ifndef LR_POOL_SLOTS
+#define LR_POOL_SLOTS 64
+#endif
+#ifndef LR_POOL_BSTART
+#define LR_POOL_BSTART 32
+#endif
+#ifndef LR_PMB_PT_TREE
+#define LR_PMB_PT_TREE 6
+#endif
+#ifndef LR_PMB_PT_FLAT
+#define LR_PMB_PT_FLAT 6
+#endif
+#ifndef LR_PMB_PTD_TREE
+#define LR_PMB_PTD_TREE 4
+#endif
+#ifndef LR_PMB_PTD_FLAT
+#define LR_PMB_PTD_FLAT 4
+#endif
+
+namespace pl {
+
+// word columns of a slot
+enum {
+  W_OX = 0, W_OY, W_OZ, W_DX, W_DY, W_DZ, W_T0, W_ID0, W_TX, W_TY, W_TZ, W_LX, W_LY, W_LZ, W_SX, W_SY, W_SZ,
+  W_CAMG, W_CAMW, W_UNX, W_UNY, W_UNZ, W_UNW, W_RNGLO, W_RNGHI, W_FLAGS, W_PT_COUNT,
+  W_D1X = W_PT_COUNT, W_D1Y, W_D1Z, W_T1, W_ID1, W_QTX, W_QTY, W_QTZ, W_QBX, W_QBY, W_QBZ, W_QPRR, W_QPC, W_QDIST, W_QSQR, W_QPDF,
+  W_PTD_COUNT
+};
+
+constexpr int kSlots = LR_POOL_SLOTS;
+static_assert(kSlots % 32 == 0 && kSlots >= 64 && kSlots <= 128, "a warp's pool holds 64, 96 or 128 paths");
+constexpr int kWords = kSlots / 32;                     // mask words per kind of work
+
+template <int INTEGRATOR>
+__host__ __device__ constexpr int words_per_slot(bool want_sumsq) {
+  return (INTEGRATOR == LR_INTEGRATOR_PT_DIRECT ? (int)W_PTD_COUNT : (int)W_PT_COUNT) + (want_sumsq ? 3 : 0);
+}
+template <int INTEGRATOR>
+__host__ __device__ constexpr int warp_words(bool want_sumsq) { return words_per_slot<INTEGRATOR>(want_sumsq) * kSlots + 32; }
+
+// Takes the first `quota` set bits of the concatenation words[rot] | words[rot + 1] | ... (cyclic): their codes
+// word * 32 + bit go to list[0, n) in that order, the bits are cleared in `words`.  Returns n (warp-uniform).  Lane j
+// looks after bit j of every word: it scatters the code to the bit's rank, and a ballot over "my bit is taken" is the
+// mask of taken bits.  `rot` (warp-uniform, < N) moves the starting word so that no part of the pool is always served
+// last — a starved slot would still hold most of its unit when the units run out, and the warp would finish it alone.
+// The caller reads list and then calls __syncwarp() before the next selection.
+template <int N>
+LR_DEV int select_take(int* list, int lane, unsigned (&words)[N], int quota, int rot) {
+  const unsigned lt = pk::lanemask_lt();
+  const unsigned bit = 1u << lane;
+  int base = 0;
+#pragma unroll
+  for (int r = 0; r < N; r++) {
+    if (r != rot) continue;                              // warp-uniform: one of the N unrolled orders runs
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const int i = (k + r) % N;                         // compile-time
+      const unsigned w = words[i];
+      const int rank = base + __popc(w & lt);
+      const bool mine = (w & bit) != 0u && rank < quota;
+      if (mine) list[rank] = i * 32 + lane;
+      words[i] = w & ~__ballot_sync(pk::kFull, mine);
+      base += __popc(w);
+    }
+  }
+  __syncwarp();
+  return min(base, quota);
+}
+
+}  // namespace pl
+
+template <int INTEGRATOR, bool TREE>
+struct PoolMinBlocks {
+  static constexpr int value = INTEGRATOR == LR_INTEGRATOR_PT_DIRECT ? (TREE ? LR_PMB_PTD_TREE : LR_PMB_PTD_FLAT) : (TREE ? LR_PMB_PT_TREE : LR_PMB_PT_FLAT);
+};
+
+template <int INTEGRATOR, bool TREE, bool COUNT, int BUILD>
+__global__ void __launch_bounds__(kBlockThreads, PoolMinBlocks<INTEGRATOR, TREE>::value)
+render_pool_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ DevParams p, float* __restrict__ out_sum,
+                   float* __restrict__ out_sumsq, unsigned long long* __restrict__ counters, unsigned int* __restrict__ next_unit) {
+  using namespace pk;
+  using namespace pl;
+  constexpr int NR = INTEGRATOR == LR_INTEGRATOR_PT_DIRECT ? 2 : 1;     // rays a vertex can issue: extension (+ shadow)
+  constexpr int NS = kSlots;
+  extern __shared__ float pool_smem[];
+  const int lane = (int)(threadIdx.x & 31);
+  const unsigned int n_units = (unsigned int)p.tiles_x * p.tiles_y * 32u * (unsigned int)p.splits;
+  const bool want_sumsq = out_sumsq != nullptr;
+  float* const pool = pool_smem + (threadIdx.x >> 5) * warp_words<INTEGRATOR>(want_sumsq);
+  int* const list = (int*)(pool + words_per_slot<INTEGRATOR>(want_sumsq) * NS);
+  constexpr int W_SQ = NR == 2 ? (int)W_PTD_COUNT : (int)W_PT_COUNT;    // sumsq columns, present only on request
+#define SLF(w) pool[(w) * NS + s]
+#define SLI(w) ((int*)pool)[(w) * NS + s]
+
+  // every slot starts fresh: no unit, no ray -> its first step fetches a unit and makes a camera ray
+  for (int s = lane; s < NS; s += 32) SLI(W_FLAGS) = 0;
+  __syncwarp();
+
+  // slot states (warp-uniform): ray r of slot s still has to traverse the BVH (pend[r * kWords + s / 32]); slot is
+  // dead (no units left).  A slot that is neither is READY: its nearest hit is known.
+  unsigned pend[NR * kWords], dead[kWords];
+#pragma unroll
+  for (int i = 0; i < NR * kWords; i++) pend[i] = 0u;
+#pragma unroll
+  for (int i = 0; i < kWords; i++) dead[i] = 0u;
+  unsigned int n_nonfinite = 0, n_retrace = 0, n_rays = 0;
+  TraceCounters tc;
+  tc.nodes = tc.tris = tc.spheres = 0;
+  int rot_a = 0, rot_b = 0;
+
+  while (true) {
+    unsigned rdy[kWords];
+    int nA = 0, nB = 0;
+#pragma unroll
+    for (int i = 0; i < kWords; i++) {
+      rdy[i] = ~(pend[i] | (NR == 2 ? pend[(NR - 1) * kWords + i] : 0u) | dead[i]);
+      nA += __popc(rdy[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NR * kWords; i++) nB += __popc(pend[i]);
+    if (nA + nB == 0) break;
+
+    if (!TREE || !(nB >= LR_POOL_BSTART || nB >= nA)) {
+      // ================================================================ phase A: one path vertex of up to 32 slots
+      const int n_sel = select_take<kWords>(list, lane, rdy, 32, rot_a);
+      rot_a = rot_a + 1 == kWords ? 0 : rot_a + 1;
+      const bool ready = lane < n_sel;
+      const int s = ready ? list[lane] : 0;
+      __syncwarp();
+      bool alive = true;
+      bool pend0 = false, pend1 = false;
+
+      F3 o = f3(0, 0, 0), T = f3(1, 1, 1), L = f3(0, 0, 0), sum = f3(0, 0, 0), sumsq = f3(0, 0, 0);
+      F3 d0 = f3(0, 0, 1), d1 = f3(0, 0, 1);
+      float t0 = 3.0e38f, t1 = 3.0e38f;
+      int id0 = -1, id1 = -1;
+      float cam_g = 1.0f, cam_w = 1.0f;
+      int4 un = make_int4(0, 0, 0, 0);
+      Pcg rng;
+      rng.state = 0;
+      F3 q_T = f3(0, 0, 0), q_brdf = f3(0, 0, 0);
+      float q_prr = 1.0f, q_point_cos = 0.0f, q_dist = 0.0f, q_sqr = 1.0f, q_pdf = 1.0f;
+      int flags = 0;
+      if (ready) {
+        o = f3(SLF(W_OX), SLF(W_OY), SLF(W_OZ));
+        d0 = f3(SLF(W_DX), SLF(W_DY), SLF(W_DZ));
+        t0 = SLF(W_T0); id0 = SLI(W_ID0);
+        T = f3(SLF(W_TX), SLF(W_TY), SLF(W_TZ));
+        L = f3(SLF(W_LX), SLF(W_LY), SLF(W_LZ));
+        sum = f3(SLF(W_SX), SLF(W_SY), SLF(W_SZ));
+        cam_g = SLF(W_CAMG); cam_w = SLF(W_CAMW);
+        un = make_int4(SLI(W_UNX), SLI(W_UNY), SLI(W_UNZ), SLI(W_UNW));
+        rng.state = (unsigned long long)(unsigned int)SLI(W_RNGLO) | ((unsigned long long)(unsigned int)SLI(W_RNGHI) << 32);
+        flags = SLI(W_FLAGS);
+        if (NR == 2) {
+          d1 = f3(SLF(W_D1X), SLF(W_D1Y), SLF(W_D1Z));
+          t1 = SLF(W_T1); id1 = SLI(W_ID1);
+          q_T = f3(SLF(W_QTX), SLF(W_QTY), SLF(W_QTZ));
+          q_brdf = f3(SLF(W_QBX), SLF(W_QBY), SLF(W_QBZ));
+          q_prr = SLF(W_QPRR); q_point_cos = SLF(W_QPC); q_dist = SLF(W_QDIST); q_sqr = SLF(W_QSQR); q_pdf = SLF(W_QPDF);
+        }
+        if (want_sumsq) sumsq = f3(SLF(W_SQ), SLF(W_SQ + 1), SLF(W_SQ + 2));
+      }
+
+      bool need_new = false;
+      bool fetch_unit = false;
+      if (ready) {
+        if (flags & F_HAS_RAY) {
+          int depth = flags & F_DEPTH_MASK;
+          bool allow_emission = (flags & F_ALLOW_EMISSION) != 0;
+          bool has_shadow_next = false;
+          const F3 d = d0;
+          if (NR == 2 && (flags & F_HAS_SHADOW)) {
+            // visibility + contribution of the shadow ray issued at the previous vertex: scene.rs:127-150
+            if (id1 != -1 && fabsf(t1 - q_dist) <= kEPS) {
+              const Surface lf = surface_at(sc, o, d1, t1, id1);  // o = the vertex position = both rays' origin
+              const float light_cos = dot(-d1, lf.n);
+              if (light_cos > 0.0f) {
+                const Mat lm = load_mat(sc, lf.mat);
+                const float g_term = q_point_cos * light_cos / q_sqr;
+                const F3 l_i = lm.emissive ? lm.emission : f3(0.0f, 0.0f, 0.0f);
+                const F3 direct = q_brdf * l_i * g_term / q_pdf;
+                // scene.rs:192 (T of the vertex, before its BSDF update); x / 1.0f == x exactly, the usual p_rr
+                L = L + q_T * (q_prr != 1.0f ? direct / q_prr : direct);
+              }
+            }
+          }
+          bool finish = false;
+          if (id0 == -1) {
+            L = L + T * sky_radiance(sc, d);                // scene.rs:29 / 43
+            finish = true;
+          } else {
+            const float t = t0;
+            const Surface sf = surface_at(sc, o, d, t, id0);
+            const Mat m = load_mat(sc, sf.mat);
+            const F3 wo = -d;
+            // emission: scene.rs:155-159 / 175-179
+            if (!(p.no_direct_emitter && depth == 0) && allow_emission && dot(wo, sf.n) > 0.0f && m.emissive)
+              L = L + T * m.emission;
+            // Russian roulette: scene.rs:64-76, 161-164
+            float prr = m.weight;
+            if (depth > p.depth_limit) prr *= scalbnf(1.0f, -(depth - p.depth_limit));
+            if (depth <= p.depth && prr > 0.0f) prr = 1.0f;
+            if (prr != 1.0f && rng.next() >= prr) {
+              finish = true;
+            } else {
+              F3 nee_dir = f3(0, 0, 1), pn = sf.n;
+              if (NR == 2) {
+                allow_emission = false;                          // every deeper vertex: no_emission = true (scene.rs:189)
+                // direct_light_radiance: scene.rs:104-125
+                if (!m.emissive && sc.n_emitters > 0) {
+                  // Objects::sample_emission objects.rs:37-51 (prefix-sum CDF, first i with roulette <= cdf[i])
+                  const float roulette = sc.emission_area * rng.next();
+                  int lo = 0, hi = sc.n_emitters - 1;
+                  while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (roulette <= __ldg(sc.emitter_cdf + mid)) hi = mid; else lo = mid + 1;
+                  }
+                  const float4 e0 = ldg4(sc.emitters + 3 * lo), e1 = ldg4(sc.emitters + 3 * lo + 1), e2 = ldg4(sc.emitters + 3 * lo + 2);
+                  const float u1 = rng.next();
+                  const float u2 = rng.next();
+                  F3 q;
+                  const float area = e1.w;
+                  if (__float_as_int(e0.w) == 0) {               // Triangle::sample triangle.rs:140-149
+                    const float mn = fminf(u1, u2), mx = fmaxf(u1, u2);
+                    q = f3(e0) * mn + f3(e1) * (1.0f - mx) + f3(e2) * (mx - mn);
+                  } else {                                       // Sphere::sample sphere.rs:79-84 + util.rs:108-116
+                    const float r1 = 2.0f * kPI * u1;
+                    const float r2 = u2 * 2.0f - 1.0f;
+                    const float r2s = sqrtf(1.0f - r2 * r2);
+                    float sn, cs;
+                    spec_sincos(r1, &sn, &cs);
+                    q = f3(e0) + e1.x * f3(cs * r2s, sn * r2s, r2);
+                  }
+                  const F3 direct_path = q - sf.pos;
+                  nee_dir = normalize(direct_path);
+                  pn = orienting_normal(wo, sf.n);
+                  if (dot(nee_dir, pn) > 0.0f) {
+                    // the shadow ray travels with the extension ray; what its resolve needs is kept
+                    q_T = T; q_prr = prr;
+                    q_point_cos = dot(nee_dir, pn);
+                    q_dist = norm(direct_path); q_sqr = sqr_norm(direct_path);
+                    q_pdf = (1.0f / area) * area / sc.emission_area;
+                    has_shadow_next = true;
+                  }
+                }
+              }
+              // material_interaction_radiance: scene.rs:78-102 (the draws come after the NEE draws, as in scene.rs:186-190)
+              F3 wi;
+              float pdf;
+              mat_sample(m, wo, sf.n, rng, wi, pdf);
+              // Material::brdf for the shadow direction (oriented normal, scene.rs:141) and for the sampled one
+              // (scene.rs:88) through ONE call site
+              F3 f_bsdf = f3(0, 0, 0);
+#pragma unroll 1
+              for (int k = (NR == 2 && has_shadow_next) ? 0 : 1; k < 2; k++) {
+                const F3 f = mat_brdf(m, wo, k == 0 ? nee_dir : wi, k == 0 ? pn : sf.n, sf.pos);
+                if (k == 0) q_brdf = f; else f_bsdf = f;
+              }
+              const F3 coef = mat_coef(m, wo, sf.n, t);
+              const float c = dot(wi, sf.n);                     // UNoriented normal (scene.rs:91)
+              T = T * (f_bsdf * coef * c / pdf);
+              if (prr != 1.0f) T = T / prr;                      // x / 1.0f == x exactly: the common case skips 3 divisions
+              o = sf.pos;                                        // no origin offset (scene.rs:94-97)
+              d0 = wi;
+              if (NR == 2 && has_shadow_next) d1 = nee_dir;
+              depth++;
+            }
+          }
+          if (finish) {
+            // main.rs:99-102
+            const F3 e = (L * cam_g) * cam_w;
+            if (!(isfinite(e.x) && isfinite(e.y) && isfinite(e.z))) n_nonfinite++;
+            sum = sum + e;
+            if (want_sumsq) sumsq = sumsq + e * e;
+            un.y += 1;
+            need_new = true;
+          }
+          flags = (flags & ~(F_DEPTH_MASK | F_ALLOW_EMISSION | F_HAS_SHADOW)) | (depth & F_DEPTH_MASK) |
+                  (allow_emission ? F_ALLOW_EMISSION : 0) | (has_shadow_next ? F_HAS_SHADOW : 0);
+        } else {
+          need_new = true;                                       // fresh slot
+        }
+
+        // ---- the unit's sample range is done: write its sums and ask for the next unit
+        if (need_new && (!(flags & F_HAS_UNIT) || un.y >= un.z)) {
+          if (flags & F_HAS_UNIT) {
+            const size_t pi = (size_t)un.x, n_px = (size_t)p.crop_w * p.crop_h;
+            if (p.splits == 1) {
+              out_sum[3 * pi + 0] += sum.x; out_sum[3 * pi + 1] += sum.y; out_sum[3 * pi + 2] += sum.z;
+              if (want_sumsq) { out_sumsq[3 * pi + 0] += sumsq.x; out_sumsq[3 * pi + 1] += sumsq.y; out_sumsq[3 * pi + 2] += sumsq.z; }
+            } else {
+              // per-split partial buffers, reduced in split order by reduce_splits_kernel (deterministic)
+              float* ps = out_sum + 3 * (n_px * un.w + pi);
+              ps[0] = sum.x; ps[1] = sum.y; ps[2] = sum.z;
+              if (want_sumsq) { float* pq = out_sumsq + 3 * (n_px * un.w + pi); pq[0] = sumsq.x; pq[1] = sumsq.y; pq[2] = sumsq.z; }
+            }
+          }
+          fetch_unit = true;
+        }
+      }
+
+      // ---- warp-aggregated unit fetch (slots that ask together receive consecutive units = pixels of one 8x4 tile)
+      {
+        bool need = fetch_unit;
+        while (true) {
+          const unsigned m = __ballot_sync(kFull, need);
+          if (m == 0u) break;
+          const int leader = __ffs(m) - 1;
+          unsigned int base = 0;
+          if (lane == leader) base = atomicAdd(next_unit, (unsigned int)__popc(m));
+          base = __shfl_sync(kFull, base, leader);
+          if (need) {
+            const unsigned int u = base + (unsigned int)__popc(m & lanemask_lt());
+            if (u >= n_units) {
+              alive = false;
+              need = false;
+            } else {
+              int lx, ly, split;
+              if (decode_unit(p, u, lx, ly, split)) {
+                const int per = p.spp_count / p.splits, rem = p.spp_count % p.splits;
+                un.x = ly * p.crop_w + lx;
+                un.y = p.spp_begin + split * per + min(split, rem);
+                un.z = un.y + per + (split < rem ? 1 : 0);
+                un.w = split;
+                flags |= F_HAS_UNIT;
+                sum = f3(0.0f, 0.0f, 0.0f);
+                sumsq = f3(0.0f, 0.0f, 0.0f);
+                need = false;
+              }
+            }
+          }
+        }
+      }
+
+      const bool go = ready && alive;
+      if (go && need_new) {
+        // next sample of the slot's pixel: camera ray (camera.rs), fresh path state
+        const int lx = un.x % p.crop_w, ly = un.x / p.crop_w;
+        const int x = p.crop_x + lx, y = p.crop_y + ly;
+        const unsigned int pixel = (unsigned int)(y * sc.cam.width + x);
+        rng.seed(p.seed, pixel, (unsigned int)un.y);
+        camera_sample_rng(sc.cam, x, y, rng, o, d0, cam_g, cam_w);
+        T = f3(1.0f, 1.0f, 1.0f);
+        L = f3(0.0f, 0.0f, 0.0f);
+        flags = (flags & ~(F_DEPTH_MASK | F_HAS_SHADOW)) | F_ALLOW_EMISSION | F_HAS_RAY;
+      }
+      // ---- inline part of Objects::intersect (objects.rs:63-65) for the new ray(s), one call site: the candidates
+      // every ray tests, then whether the ray can reach the tree at all; if it can, the ray is left pending
+#pragma unroll 1
+      for (int r = 0; r < NR; r++) {
+        const bool on = go && (r == 0 || (flags & F_HAS_SHADOW));
+        if (!__any_sync(kFull, on)) continue;
+        if (on) {
+          const F3 d = r == 0 ? d0 : d1;
+          const F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+          float t = 3.0e38f;
+          int id = -1;
+          flat_hits<COUNT>(sc, o, d, inv, t, id, tc);
+          n_rays++;
+          const bool pd = TREE && sc.n_nodes > 0 && bvh_bounds_hit(sc, o, inv, t < 3.0e38f ? t * 1.0001f + 1e-4f : 3.0e38f);
+          if (r == 0) { t0 = t; id0 = id; pend0 = pd; } else { t1 = t; id1 = id; pend1 = pd; }
+        }
+      }
+
+      if (go) {
+        SLF(W_OX) = o.x; SLF(W_OY) = o.y; SLF(W_OZ) = o.z;
+        SLF(W_DX) = d0.x; SLF(W_DY) = d0.y; SLF(W_DZ) = d0.z;
+        SLF(W_T0) = t0; SLI(W_ID0) = id0;
+        SLF(W_TX) = T.x; SLF(W_TY) = T.y; SLF(W_TZ) = T.z;
+        SLF(W_LX) = L.x; SLF(W_LY) = L.y; SLF(W_LZ) = L.z;
+        SLF(W_SX) = sum.x; SLF(W_SY) = sum.y; SLF(W_SZ) = sum.z;
+        SLF(W_CAMG) = cam_g; SLF(W_CAMW) = cam_w;
+        SLI(W_UNX) = un.x; SLI(W_UNY) = un.y; SLI(W_UNZ) = un.z; SLI(W_UNW) = un.w;
+        SLI(W_RNGLO) = (int)(unsigned int)rng.state; SLI(W_RNGHI) = (int)(unsigned int)(rng.state >> 32);
+        SLI(W_FLAGS) = flags;
+        if (NR == 2) {
+          SLF(W_D1X) = d1.x; SLF(W_D1Y) = d1.y; SLF(W_D1Z) = d1.z;
+          SLF(W_T1) = t1; SLI(W_ID1) = id1;
+          SLF(W_QTX) = q_T.x; SLF(W_QTY) = q_T.y; SLF(W_QTZ) = q_T.z;
+          SLF(W_QBX) = q_brdf.x; SLF(W_QBY) = q_brdf.y; SLF(W_QBZ) = q_brdf.z;
+          SLF(W_QPRR) = q_prr; SLF(W_QPC) = q_point_cos; SLF(W_QDIST) = q_dist; SLF(W_QSQR) = q_sqr; SLF(W_QPDF) = q_pdf;
+        }
+        if (want_sumsq) { SLF(W_SQ) = sumsq.x; SLF(W_SQ + 1) = sumsq.y; SLF(W_SQ + 2) = sumsq.z; }
+      }
+      // new slot states
+      const unsigned bit = 1u << (s & 31);
+      const int w = s >> 5;
+#pragma unroll
+      for (int i = 0; i < kWords; i++) {
+        pend[i] |= __reduce_or_sync(kFull, (go && pend0 && w == i) ? bit : 0u);
+        if (NR == 2) pend[(NR - 1) * kWords + i] |= __reduce_or_sync(kFull, (go && pend1 && w == i) ? bit : 0u);
+        dead[i] |= __reduce_or_sync(kFull, (ready && !alive && w == i) ? bit : 0u);
+      }
+    } else {
+      // ================================================================ phase B
+      // a batch of up to 32 pending rays (extension or shadow) traverses the BVH: one loop that advances every lane by
+      // at most one inner node and one triangle test per iteration (trav_step), optimistic accept, the nearest hit gated
+      // once at the end, strict re-trace in the rare case the gate rejects it.  (Refilling idle lanes from the pool
+      // inside this loop was measured too: the bookkeeping costs more than the width it keeps, profiles/r01_e_*.)
+      const int n_sel = select_take<NR * kWords>(list, lane, pend, 32, rot_b);
+      rot_b = rot_b + 1 == NR * kWords ? 0 : rot_b + 1;
+      if (lane < n_sel) {
+        const int item = list[lane];
+        const int s = item % NS;
+        const bool shadow = NR == 2 && item >= NS;
+        const F3 o = f3(SLF(W_OX), SLF(W_OY), SLF(W_OZ));
+        const F3 d = shadow ? f3(SLF(W_D1X), SLF(W_D1Y), SLF(W_D1Z)) : f3(SLF(W_DX), SLF(W_DY), SLF(W_DZ));
+        const F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        float t = shadow ? SLF(W_T1) : SLF(W_T0);
+        int id = shadow ? SLI(W_ID1) : SLI(W_ID0);
+        bvh_traverse_unified<COUNT>(sc, o, d, inv, t, id, tc);
+        if (id >= 0 && id < sc.n_bvh_tris && !bvh_hit_is_gated(sc, o, inv, id)) {
+          trace_strict<COUNT>(sc, o, d, &t, &id, &tc);
+          n_retrace++;
+        }
+        if (shadow) { SLF(W_T1) = t; SLI(W_ID1) = id; } else { SLF(W_T0) = t; SLI(W_ID0) = id; }
+      }
+    }
+    __syncwarp();
+  }
+#undef SLF
+#undef SLI
+
+  // counters: warp reduce, one atomic per warp
+  n_rays = warp_sum_u(n_rays);
+  n_nonfinite = warp_sum_u(n_nonfinite);
+  n_retrace = warp_sum_u(n_retrace);
+  if (COUNT) { tc.nodes = warp_sum_u(tc.nodes); tc.tris = warp_sum_u(tc.tris); tc.spheres = warp_sum_u(tc.spheres); }
+  if (lane == 0) {
+    if (n_rays) atomicAdd(counters + C_RAYS, (unsigned long long)n_rays);
+    if (n_nonfinite) atomicAdd(counters + C_NONFINITE, (unsigned long long)n_nonfinite);
+    if (n_retrace) atomicAdd(counters + C_RETRACE, (unsigned long long)n_retrace);
+    if (COUNT) {
+      atomicAdd(counters + C_NODES, (unsigned long long)tc.nodes);
+      atomicAdd(counters + C_TRIS, (unsigned long long)tc.tris);
+      atomicAdd(counters + C_SPHERES, (unsigned long long)tc.spheres);
+    }
+  }
+}
+
+// one launch = the whole sample range of every unit: a persistent grid that fills the SMs
+template <int INTEGRATOR, bool TREE, bool COUNT, int BUILD>
+cudaError_t launch_pool_one(const DevScene& sc, const DevParams& p, float* out_sum, float* out_sumsq, unsigned long long* counters,
+                            unsigned int* next_unit, int sm_count, cudaStream_t stream) {
+  auto kernel = render_pool_kernel<INTEGRATOR, TREE, COUNT, BUILD>;
+  const size_t smem = (size_t)(kBlockThreads / 32) * pl::warp_words<INTEGRATOR>(out_sumsq != nullptr) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kBlockThreads, smem) != cudaSuccess || nb <= 0) nb = 2;
+  // a warp serves kSlots units at a time
+  const long long units = (long long)p.tiles_x * p.tiles_y * 32 * p.splits;
+  const long long per_block = (long long)(kBlockThreads / 32) * pl::kSlots;
+  const long long want = (units + per_block - 1) / per_block;
+  const unsigned int blocks = (unsigned int)std::max<long long>(1, std::min<long long>(want, (long long)nb * sm_count));
+  kernel<<<blocks, kBlockThreads, smem, stream>>>(sc, p, out_sum, out_sumsq, counters, next_unit);
+  return cudaGetLastError();
+}
+
+}  // namespace lr

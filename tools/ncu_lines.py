@@ -7,7 +7,7 @@ rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 45
 # every object of the in-tree build holds one cubin; disassemble them all and keep the one with the kernel
 dis = []
-for obj in sorted(glob.glob(os.path.join(ROOT, "lumillyrender_b200", "build", "*.o"))):
+for obj in sorted(glob.glob(os.environ.get("NCU_OBJ_GLOB") or os.path.join(ROOT, "lumillyrender_b200", "build", "*.o"))):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", obj], cwd=tmp, capture_output=True)
     for cub in glob.glob(tmp + "/*.cubin"):

@@ -65,6 +65,9 @@ for r in rows[2:]:
         key = "dp:" + fn(s_[1])
     elif s_[0] == "persistent.cuh":
         key = "pk:%d" % (s_[1] // 25 * 25)
+    elif s_[0] in ("pool.cuh", "cpool.cuh"):
+        g = int(os.environ.get("REGION_LINES", "10"))
+        key = "%s:%d" % (s_[0], s_[1] // g * g)
     else:
         key = s_[0]
     wi, ti, sm = int(r[ix["Instructions Executed"]]), int(r[ix["Thread Instructions Executed"]]), int(r[ix["# Samples"]])
@@ -72,5 +75,5 @@ for r in rows[2:]:
     a[0] += wi; a[1] += ti; a[2] += sm
     tot[0] += wi; tot[1] += ti; tot[2] += sm
 print("total warp instr %.3e  thread instr %.3e  avg threads %.2f" % (tot[0], tot[1], tot[1] / tot[0]))
-for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:32]:
+for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(os.environ.get("REGION_TOP", "32"))]:
     print("%-46s warp-instr %6.2f%%  thr %5.1f  samples %5.2f%%" % (k, 100 * a[0] / tot[0], a[1] / max(a[0], 1), 100 * a[2] / tot[2]))

@@ -81,7 +81,9 @@ def build_library(force=False, verbose=False, extra=(), obj_dir=None):
                 o = os.path.join(obj_dir, "persistent_i%d_t%d_g%d.o" % (integ, tree, ggx))
                 objs.append(o)
                 defs = ["-DLR_INST_INTEGRATOR=%d" % integ, "-DLR_INST_TREE=%d" % tree, "-DLR_INST_GGX=%d" % ggx, "-DLR_OUTLINE_COLD"]
-                if tree:
+                if tree and integ == 1:
+                    # vector / scalar quotients out of line: +4.6 % for the one-path-per-lane kernel over a BVH (it is
+                    # instruction-fetch bound), -4.5 % for the pool kernel (pt over a BVH): profiles/r01_e_ab_s50.txt
                     defs.append("-DLR_DIV_OUT_OF_LINE")
                 if not ggx:
                     defs.append("-DLR_GGX_OUT_OF_LINE")

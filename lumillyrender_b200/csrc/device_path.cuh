@@ -40,8 +40,8 @@ LR_DEV F3 operator-(F3 a, F3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
 LR_DEV F3 operator*(F3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
 LR_DEV F3 operator*(float s, F3 a) { return f3(s * a.x, s * a.y, s * a.z); }
 LR_DEV F3 operator*(F3 a, F3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
-// IEEE quotient of a vector by a scalar.  In the kernels that traverse a BVH the three divisions live in ONE out-of-line
-// function (LR_DIV_OUT_OF_LINE, set by build.py for those translation units): ~20 inlined copies of 3 x 14 instructions
+// IEEE quotient of a vector by a scalar.  In the one-path-per-lane kernel for pt-direct over a BVH the three divisions live in ONE
+// out-of-line function (LR_DIV_OUT_OF_LINE, set by build.py for that translation unit): ~20 inlined copies of 3 x 14 instructions
 // are a fifth of the kernel's code, and the kernel is instruction-fetch bound (A/B, profiles/r01_c_ab_s22.txt: +4.6 % on
 // sample.toml; the flat-only kernels are 3 % faster with the divisions inlined).
 #ifdef LR_DIV_OUT_OF_LINE
@@ -73,12 +73,12 @@ LR_DEV void spec_sincos(float x, float* sn, float* cs) {
   const float z = r * r;
   const float s = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
   const float c = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z - 0.5f * z + 1.0f;
-  switch (k & 3) {
-    case 0: *sn = s; *cs = c; break;
-    case 1: *sn = c; *cs = -s; break;
-    case 2: *sn = -s; *cs = -c; break;
-    default: *sn = -c; *cs = s; break;
-  }
+  // quadrant k & 3: (s, c), (c, -s), (-s, -c), (-c, s) — as selects and exact negations, not a four-way branch (the
+  // lanes of a warp are spread over all four quadrants: ncu showed this function at 12 of 32 lanes)
+  const bool swap = (k & 1) != 0;
+  const float a = swap ? c : s, b = swap ? s : c;
+  *sn = (k & 2) ? -a : a;
+  *cs = ((k + 1) & 2) ? -b : b;
 }
 
 // ------------------------------------------------------------------ RNG (replaces rand::random)

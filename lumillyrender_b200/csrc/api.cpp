@@ -327,6 +327,9 @@ static int resolve_params(const LrScene* s, const LrRenderParams* p, DevParams& 
   const char* e_dt = std::getenv("LR_DEFER_THRESH");
   dp.defer_iters = e_di ? std::max(1, std::atoi(e_di)) : 3;
   dp.defer_thresh = e_dt ? std::max(1, std::min(32, std::atoi(e_dt))) : 12;
+  // both organisations of the render kernel are built for scenes with a BVH; tests render with each and compare bits
+  const char* e_org = std::getenv("LR_ORGANISATION");
+  dp.organisation = !e_org ? 0 : (std::strcmp(e_org, "persistent") == 0 ? 1 : (std::strcmp(e_org, "pool") == 0 ? 2 : 0));
 
   return LR_OK;
 }

@@ -52,6 +52,7 @@ struct DevParams {
   int splits;
   int tiles_x, tiles_y;                  // 8x4 pixel tiles over the crop window
   int defer_iters, defer_thresh;         // path vertices per phase A; suspended lanes that end it early (persistent.cuh)
+  int organisation;                      // 0 = the build's measured best, 1 = one path per lane (persistent.cuh), 2 = pool (pool.cuh); BVH scenes only
 };
 
 // device counter block (unsigned long long each)

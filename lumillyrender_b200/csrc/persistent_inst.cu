@@ -10,20 +10,12 @@
 #error "compile with -DLR_INST_INTEGRATOR=0|1 -DLR_INST_TREE=0|1 -DLR_INST_GGX=0|1"
 #endif
 
-// Which organisation runs a build (A/B on one box, profiles/r01_e_ab_*.txt): the pool kernel (pool.cuh) for pure path
-// tracing over a BVH (sample.toml: 49.0 -> 39.9 ms), the one-path-per-lane kernel (persistent.cuh) for the flat-only
-// scenes (no phase B to feed) and for pt-direct over a BVH, whose 42-word slots leave room for too few warps
-// (welcome-2018: 52.7 ms against 62.7 ms).  LR_FORCE_POOL=0|1 overrides for A/B builds.
-#if defined(LR_FORCE_POOL)
-#define LR_USE_POOL LR_FORCE_POOL
-#else
+// Which organisation runs a build by default (A/B on one box, profiles/r01_e_ab_*.txt): the pool kernel (pool.cuh) for
+// pure path tracing over a BVH (sample.toml: 49.0 -> 37.9 ms), the one-path-per-lane kernel (persistent.cuh) for the
+// flat-only scenes (no phase B to feed) and for pt-direct over a BVH, whose 42-word slots leave room for too few warps
+// (welcome-2018: 52.7 ms against 62.7 ms).  The units for scenes with a BVH hold BOTH organisations: DevParams.organisation
+// (LR_ORGANISATION=persistent|pool, api.cpp) overrides the default so that tests can compare their images bit for bit.
 #define LR_USE_POOL (LR_INST_TREE && LR_INST_INTEGRATOR == LR_INTEGRATOR_PT)
-#endif
-#if LR_USE_POOL
-#define LR_LAUNCH_ONE launch_pool_one
-#else
-#define LR_LAUNCH_ONE launch_persistent_one
-#endif
 
 namespace lr {
 
@@ -33,11 +25,23 @@ namespace lr {
 cudaError_t LR_PASTE(launch_persistent_i, LR_INST_INTEGRATOR, LR_INST_TREE, LR_INST_GGX)(
     const DevScene& sc, const DevParams& p, bool count, float* out_sum, float* out_sumsq, unsigned long long* counters,
     unsigned int* next_unit, int sm_count, cudaStream_t stream) {
-#if LR_INST_TREE && LR_INST_GGX
-  if (count) return LR_LAUNCH_ONE<LR_INST_INTEGRATOR, true, true, LR_INST_GGX>(sc, p, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
+#if LR_INST_TREE
+  const bool pool = p.organisation == 2 || (p.organisation == 0 && LR_USE_POOL);
+#if LR_INST_GGX
+  // the instrumented kernel: the build's default organisation only
+#if LR_USE_POOL
+  if (count) return launch_pool_one<LR_INST_INTEGRATOR, true, true, LR_INST_GGX>(sc, p, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
+#else
+  if (count) return launch_persistent_one<LR_INST_INTEGRATOR, true, true, LR_INST_GGX>(sc, p, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
+#endif
 #endif
   (void)count;
-  return LR_LAUNCH_ONE<LR_INST_INTEGRATOR, LR_INST_TREE != 0, false, LR_INST_GGX>(sc, p, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
+  if (pool) return launch_pool_one<LR_INST_INTEGRATOR, true, false, LR_INST_GGX>(sc, p, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
+  return launch_persistent_one<LR_INST_INTEGRATOR, true, false, LR_INST_GGX>(sc, p, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
+#else
+  (void)count;
+  return launch_persistent_one<LR_INST_INTEGRATOR, false, false, LR_INST_GGX>(sc, p, out_sum, out_sumsq, counters, next_unit, sm_count, stream);
+#endif
 }
 
 }  // namespace lr

@@ -227,6 +227,23 @@ def test_kernel_organisations_agree_bit_for_bit(scenes, monkeypatch, name, spp):
     assert np.array_equal(default, a[0], equal_nan=True) and st["rays"] == a[3]
 
 
+def test_pool_kernel_small_work(scenes):
+    """The pool kernel (sample.toml: pt over a BVH) when there is less work than one warp's pool holds: single-pixel
+    and single-row crops, one sample per pixel, more splits than samples — same pixels as the full render."""
+    d, s, o = scenes("sample")
+    full, _, st = s.render(spp=3, seed=11, splits=1)
+    for crop in ((0, 0, 1, 1), (159, 159, 1, 1), (3, 77, 157, 1), (80, 0, 1, 160), (5, 6, 7, 9)):
+        x, y, w, h = crop
+        c, _, _ = s.render(spp=3, seed=11, splits=1, crop=crop)
+        assert c.shape == (h, w, 3) and np.array_equal(c, full[y:y + h, x:x + w]), crop
+    one, _, st1 = s.render(spp=1, seed=11, splits=1)
+    many, _, stm = s.render(spp=1, seed=11, splits=8)            # clamped to the sample count
+    assert stm["splits"] == 1 and np.array_equal(one, many) and st1["rays"] == stm["rays"]
+    lo, _, _ = s.render(spp=2, spp_begin=0, seed=11, splits=1)
+    hi, _, _ = s.render(spp=1, spp_begin=2, seed=11, splits=1)
+    assert np.allclose((lo * 2 + hi) / 3, full, rtol=1e-5, atol=1e-6)
+
+
 def test_error_paths(scenes, lr):
     from lumillyrender_b200.capi import LumillyError
     d, s, o = scenes("primitive")

@@ -200,6 +200,19 @@ int lr_render_accumulate_device(const LrScene* scene, const LrRenderParams* para
 /* fetch + reset the device counters of the accumulate calls issued so far (synchronises the stream) */
 int lr_stats_fetch(const LrScene* scene, void* cuda_stream, LrStats* stats);
 
+/* lr_render_multi: the whole loop of main.rs:70-132 on SEVERAL GPUs of one box from one process (what a
+   single-process host such as the reference's `main` calls; one process per GPU uses
+   lr_render_accumulate_device instead).  The scene is uploaded to every listed device; the sample range
+   [spp_begin, spp_begin + spp_count) is cut into n_devices consecutive ranges whose sizes differ by <= 1
+   (samples are counter-indexed, so any device can render any range); the devices render concurrently, each
+   into its own per-pixel sum buffer; then ONE kernel on devices[0] reads the peers' buffers over NVLink
+   (peer access; staged copies where peer access is unavailable), adds them in list order and divides by
+   spp_count.  out_rgb / out_sumsq / stats as lr_render (stats are totals, kernel_ms the slowest device's).
+   1 <= n_devices <= 8, device ids distinct.  The result for a given device COUNT is bit-reproducible and
+   differs from other counts only by fp32 summation order. */
+int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* params, int32_t n_devices, const int32_t* devices,
+                    float* out_rgb, float* out_sumsq, LrStats* stats);
+
 /* ---- parity probe: nearest hit of the primary ray through every film pixel with the
  * sensor jitter fixed to (u,v) and the aperture sample fixed to (ua,va).
  * prim[i] = primitive id or -1, t[i] = Intersection.distance (bvh.rs:131-141).      */

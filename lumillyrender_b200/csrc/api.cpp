@@ -437,6 +437,126 @@ int lr_render(const LrScene* s, const LrRenderParams* p, float* out_rgb, float* 
   return rc;
 }
 
+int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_devices, const int32_t* devices, float* out_rgb,
+                    float* out_sumsq, LrStats* stats) {
+  if (!desc || !p || !devices || !out_rgb) return fail(LR_ERR_INVALID, "null argument");
+  if (n_devices < 1 || n_devices > kMaxPeers) return fail(LR_ERR_INVALID, "lr_render_multi takes 1..8 devices");
+  if (p->spp_count <= 0 || p->spp_begin < 0) return fail(LR_ERR_INVALID, "spp range must be non-empty and non-negative");
+  int n_visible = 0;
+  if (cudaGetDeviceCount(&n_visible) != cudaSuccess || n_visible <= 0)
+    return fail(LR_ERR_NO_DEVICE, "no CUDA device available; liblumilly_b200 has no CPU fallback");
+  for (int i = 0; i < n_devices; i++) {
+    if (devices[i] < 0 || devices[i] >= n_visible) return fail(LR_ERR_INVALID, "device index out of range");
+    for (int j = 0; j < i; j++) if (devices[j] == devices[i]) return fail(LR_ERR_INVALID, "device listed twice");
+  }
+  int prev_device = 0;
+  cudaGetDevice(&prev_device);
+  const int home = g_device >= 0 ? g_device : devices[0];
+
+  std::vector<LrScene*> scenes(n_devices, nullptr);
+  std::vector<LrRenderParams> parts(n_devices, *p);
+  std::vector<cudaEvent_t> done(n_devices, nullptr);
+  float* staged = nullptr;                                 // on devices[0]: copies of buffers it cannot map
+  size_t n = 0;
+  int rc = LR_OK;
+  LrStats total;
+  std::memset(&total, 0, sizeof(total));
+  do {
+    // ---- upload and launch: every call below is asynchronous, so the devices render concurrently
+    const int per = p->spp_count / n_devices, rem = p->spp_count % n_devices;
+    for (int i = 0; i < n_devices && rc == LR_OK; i++) {
+      if ((rc = lr_init(devices[i])) != LR_OK) break;      // cudaSetDevice + the non-trimming memory pool
+      if ((rc = lr_scene_create(desc, &scenes[i])) != LR_OK) break;
+      const LrScene* s = scenes[i];
+      parts[i].spp_begin = p->spp_begin + i * per + std::min(i, rem);
+      parts[i].spp_count = per + (i < rem ? 1 : 0);
+      DevParams dp;
+      LrRenderParams probe = parts[i];
+      if (probe.spp_count == 0) probe.spp_count = 1;       // more devices than samples: this one only contributes zeros
+      if ((rc = resolve_params(s, &probe, dp)) != LR_OK) break;
+      n = (size_t)dp.crop_w * dp.crop_h * 3;
+      if ((rc = ensure_scratch(&s->d_film, &s->film_floats, n)) != LR_OK) break;
+      if (out_sumsq && (rc = ensure_scratch(&s->d_film_sq, &s->film_sq_floats, n)) != LR_OK) break;
+      cudaError_t e = cudaMemsetAsync(s->d_film, 0, n * sizeof(float), 0);
+      if (e == cudaSuccess && out_sumsq) e = cudaMemsetAsync(s->d_film_sq, 0, n * sizeof(float), 0);
+      if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("cudaMemsetAsync: ") + cudaGetErrorString(e)); break; }
+      if (parts[i].spp_count > 0 &&
+          (rc = lr_render_accumulate_device(s, &parts[i], s->d_film, out_sumsq ? s->d_film_sq : nullptr, nullptr)) != LR_OK) break;
+      e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventRecord(done[i], 0);
+      if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("cudaEventRecord: ") + cudaGetErrorString(e)); break; }
+    }
+    if (rc != LR_OK) break;
+
+    // ---- reduce + normalise on devices[0]
+    cudaError_t e = cudaSetDevice(devices[0]);
+    PeerBuffers sum_src, sq_src;
+    sum_src.count = sq_src.count = n_devices;
+    size_t staged_floats = 0;
+    std::vector<int> mapped(n_devices, 1);
+    for (int i = 1; i < n_devices && e == cudaSuccess; i++) {
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, devices[0], devices[i]);
+      if (can) {
+        const cudaError_t pe = cudaDeviceEnablePeerAccess(devices[i], 0);
+        if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (pe != cudaSuccess) { can = 0; cudaGetLastError(); }
+      }
+      mapped[i] = can;
+      if (!can) staged_floats += n * (out_sumsq ? 2 : 1);
+    }
+    if (e == cudaSuccess && staged_floats > 0) e = dev_alloc((void**)&staged, staged_floats * sizeof(float));
+    float* stage_next = staged;
+    for (int i = 0; i < n_devices && e == cudaSuccess; i++) {
+      e = cudaStreamWaitEvent(0, done[i], 0);              // devices[0]'s stream waits for device i's render
+      if (e != cudaSuccess) break;
+      sum_src.p[i] = scenes[i]->d_film;
+      sq_src.p[i] = out_sumsq ? scenes[i]->d_film_sq : nullptr;
+      if (!mapped[i]) {
+        e = cudaMemcpyPeerAsync(stage_next, devices[0], scenes[i]->d_film, devices[i], n * sizeof(float), 0);
+        sum_src.p[i] = stage_next; stage_next += n;
+        if (e == cudaSuccess && out_sumsq) {
+          e = cudaMemcpyPeerAsync(stage_next, devices[0], scenes[i]->d_film_sq, devices[i], n * sizeof(float), 0);
+          sq_src.p[i] = stage_next; stage_next += n;
+        }
+      }
+    }
+    if (e == cudaSuccess) e = launch_reduce_peers(scenes[0]->d_film, sum_src, n, (float)p->spp_count, 0);   // main.rs:104
+    if (e == cudaSuccess && out_sumsq) e = launch_reduce_peers(scenes[0]->d_film_sq, sq_src, n, 0.0f, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(out_rgb, scenes[0]->d_film, n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out_sumsq) e = cudaMemcpy(out_sumsq, scenes[0]->d_film_sq, n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("lr_render_multi reduce: ") + cudaGetErrorString(e)); break; }
+
+    // ---- statistics: totals over the devices, the slowest device's kernel time
+    for (int i = 0; i < n_devices && rc == LR_OK; i++) {
+      if (cudaSetDevice(devices[i]) != cudaSuccess) { rc = fail(LR_ERR_CUDA, "cudaSetDevice failed"); break; }
+      LrStats st;
+      if ((rc = lr_stats_fetch(scenes[i], nullptr, &st)) != LR_OK) break;
+      total.rays += st.rays; total.samples += st.samples; total.nodes_visited += st.nodes_visited; total.tris_tested += st.tris_tested;
+      total.spheres_tested += st.spheres_tested; total.nonfinite_samples += st.nonfinite_samples; total.gate_retraces += st.gate_retraces;
+      total.kernel_ms = std::max(total.kernel_ms, st.kernel_ms);
+      total.launches += st.launches;
+      total.splits = std::max(total.splits, st.splits);
+    }
+    total.launches += out_sumsq ? 2 : 1;
+  } while (0);
+
+  const std::string err = g_error;                         // clean-up must not clobber the message
+  for (int i = 0; i < n_devices; i++) {
+    if (!scenes[i] && !done[i]) continue;
+    cudaSetDevice(devices[i]);
+    cudaDeviceSynchronize();
+    if (done[i]) cudaEventDestroy(done[i]);
+    if (i == 0 && staged) dev_free(staged);
+    lr_scene_destroy(scenes[i]);
+  }
+  cudaSetDevice(home >= 0 && home < n_visible ? home : prev_device);
+  g_device = home;
+  if (rc != LR_OK) { g_error = err; return rc; }
+  if (stats) *stats = total;
+  return LR_OK;
+}
+
 int lr_trace_primary(const LrScene* s, float u, float v, float ua, float va, int32_t* prim, float* t) {
   if (!s || !prim || !t) return fail(LR_ERR_INVALID, "null argument");
   if (int rc = ensure_device()) return rc;

@@ -5,6 +5,7 @@
 // panics become a message on stderr and a non-zero exit status.
 //
 // Extra, optional arguments (not in the reference):  --spp N  --resolution WxH  --seed S  --device D
+//   --gpus N (render on devices D..D+N-1 of this box from this one process: lr_render_multi, samples sharded by index)
 //   --assets DIR (root that mesh/IBL paths are resolved against; default: the current directory, like the reference)
 #include <sys/stat.h>
 
@@ -37,7 +38,7 @@ int main(int argc, char** argv) {
   std::printf("start: %s\n", stamp("%Y-%m-%dT%H:%M:%S%z").c_str());
   const char* scene_path = nullptr;
   const char* assets = nullptr;
-  int spp = -1, ow = 0, oh = 0, device = 0;
+  int spp = -1, ow = 0, oh = 0, device = 0, gpus = 1;
   unsigned long long seed = 0;
   for (int i = 1; i < argc; i++) {
     const std::string a = argv[i];
@@ -49,6 +50,7 @@ int main(int argc, char** argv) {
     else if (a == "--resolution") { if (std::sscanf(need("--resolution"), "%dx%d", &ow, &oh) != 2) { std::fprintf(stderr, "error: --resolution WxH\n"); return 2; } }
     else if (a == "--seed") seed = std::strtoull(need("--seed"), nullptr, 10);
     else if (a == "--device") device = std::atoi(need("--device"));
+    else if (a == "--gpus") gpus = std::atoi(need("--gpus"));
     else if (a == "--assets") assets = need("--assets");
     else if (!scene_path) scene_path = argv[i];
     else { std::fprintf(stderr, "error: unexpected argument `%s`\n", argv[i]); return 2; }
@@ -73,14 +75,20 @@ int main(int argc, char** argv) {
   std::printf("bvh construction: %gs\n", cfg.bvh_build_seconds);                 // description.rs:70-73
 
   LrScene* scene = nullptr;
-  if (lr_scene_create(lr_host_scene_desc(hs), &scene) != LR_OK) return die("uploading scene");
+  if (gpus <= 1 && lr_scene_create(lr_host_scene_desc(hs), &scene) != LR_OK) return die("uploading scene");
   LrRenderParams p;
   std::memset(&p, 0, sizeof(p));
   p.integrator = cfg.integrator; p.spp_begin = 0; p.spp_count = cfg.samples;
   p.depth = cfg.depth; p.depth_limit = cfg.depth_limit; p.no_direct_emitter = cfg.no_direct_emitter; p.seed = seed;
   std::vector<float> img((size_t)cfg.width * cfg.height * 3);
   LrStats st;
-  if (lr_render(scene, &p, img.data(), nullptr, &st) != LR_OK) return die("rendering");
+  if (gpus > 1) {
+    if (gpus > 8) { std::fprintf(stderr, "error: --gpus takes 1..8\n"); return 2; }
+    int32_t devices[8];
+    for (int i = 0; i < gpus; i++) devices[i] = device + i;
+    std::printf("gpus: %d (devices %d..%d, samples sharded by index, one peer-reading reduce)\n", gpus, device, device + gpus - 1);
+    if (lr_render_multi(lr_host_scene_desc(hs), &p, gpus, devices, img.data(), nullptr, &st) != LR_OK) return die("rendering");
+  } else if (lr_render(scene, &p, img.data(), nullptr, &st) != LR_OK) return die("rendering");
   std::printf("render: %.3f ms on the GPU, %.1f Msamples/s, %.1f Mrays/s, %llu non-finite samples\n", st.kernel_ms,
               st.samples / (st.kernel_ms * 1e3), st.rays / (st.kernel_ms * 1e3), (unsigned long long)st.nonfinite_samples);
 

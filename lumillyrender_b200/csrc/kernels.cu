@@ -24,6 +24,18 @@ __global__ void scale_kernel(float* __restrict__ dst, size_t n, float divisor) {
   if (i < n) dst[i] = dst[i] / divisor;   // `estimated_sum / spp as f32` (main.rs:104): a true division
 }
 
+// K7 across GPUs, fused: one kernel on the first device reads every device's per-pixel sums — its own and, through
+// peer access over NVLink, the others' — adds them in device order (a fixed order: the image does not depend on which
+// GPU finished first) and divides by the total sample count (main.rs:104; divisor <= 0: sums only, for the sum of
+// squares).  32 MB per peer at 1920x1370: a few hundred microseconds next to a render of tens of milliseconds.
+__global__ void reduce_peers_kernel(float* __restrict__ dst, PeerBuffers src, size_t n, float divisor) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = src.p[0][i];
+  for (int k = 1; k < src.count; k++) acc = acc + src.p[k][i];
+  dst[i] = divisor > 0.0f ? acc / divisor : acc;
+}
+
 // parity probe: nearest hit of the primary ray of every film pixel with fixed random numbers
 __global__ void __launch_bounds__(kBlockThreads)
 primary_kernel(const __grid_constant__ DevScene sc, int tiles_x, int tiles_y, float u, float v, float ua, float va,
@@ -112,6 +124,11 @@ cudaError_t launch_reduce_splits(float* dst, const float* partial, size_t n, int
 
 cudaError_t launch_scale(float* dst, size_t n, float divisor, cudaStream_t stream) {
   scale_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, stream>>>(dst, n, divisor);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_peers(float* dst, const PeerBuffers& src, size_t n, float divisor, cudaStream_t stream) {
+  reduce_peers_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, stream>>>(dst, src, n, divisor);
   return cudaGetLastError();
 }
 

@@ -16,6 +16,10 @@ LR_DECL_INST(launch_persistent_i1_t0_g1) LR_DECL_INST(launch_persistent_i1_t1_g1
 #undef LR_DECL_INST
 cudaError_t launch_reduce_splits(float* dst, const float* partial, size_t n, int splits, cudaStream_t stream);
 cudaError_t launch_scale(float* dst, size_t n, float divisor, cudaStream_t stream);
+// lr_render_multi: the per-device sum buffers (peer pointers), added in order by one kernel on the first device
+constexpr int kMaxPeers = 8;
+struct PeerBuffers { const float* p[kMaxPeers]; int count; };
+cudaError_t launch_reduce_peers(float* dst, const PeerBuffers& src, size_t n, float divisor, cudaStream_t stream);
 cudaError_t launch_primary(const DevScene& sc, float u, float v, float ua, float va, int* prim, float* t, cudaStream_t stream);
 cudaError_t launch_rays(const DevScene& sc, long long n, const float* org, const float* dir, int* prim, float* t, float* nout,
                         cudaStream_t stream);

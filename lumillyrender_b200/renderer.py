@@ -81,6 +81,19 @@ class Description:
     def scene(self):
         return Scene(self)
 
+    def render_multi(self, devices, sumsq=False, **kw):
+        """One process, several GPUs (lr_render_multi): the scene goes to every device in `devices`, the sample range is
+        sharded by sample index, one kernel on devices[0] sums the peers' buffers over NVLink and divides by spp.
+        Returns (mean image, sumsq or None, stats dict) like Scene.render."""
+        p = kw.pop("params", None) or params_from_config(self.config, **kw)
+        shape = (p.crop_h, p.crop_w, 3) if p.crop_w > 0 else (self.config.height, self.config.width, 3)
+        img = np.empty(shape, dtype=np.float32)
+        sq = np.empty(shape, dtype=np.float32) if sumsq else None
+        st = LrStats()
+        dev = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        check(self._lib.lr_render_multi(self.desc, C.byref(p), len(devices), dev, _fptr(img), _fptr(sq) if sumsq else None, C.byref(st)))
+        return img, sq, st.as_dict()
+
     def close(self):
         if self._h:
             self._lib.lr_host_scene_free(self._h)

@@ -244,6 +244,42 @@ def test_pool_kernel_small_work(scenes):
     assert np.allclose((lo * 2 + hi) / 3, full, rtol=1e-5, atol=1e-6)
 
 
+def test_render_multi_single_process(scenes, lr, gpu):
+    """lr_render_multi (one process, the scene on every listed device, sample ranges sharded, one peer-reading reduce
+    kernel): with one device it is lr_render bit for bit; with two it equals the single-device render up to the fp32
+    order of the cross-device sum, ray counts add up exactly, and it is reproducible.  Error paths return codes."""
+    from lumillyrender_b200.capi import LumillyError
+    torch = pytest.importorskip("torch")
+    d, s, o = scenes("sample")
+    ref, ref_sq, st = s.render(spp=6, seed=13, splits=1, sumsq=True)
+    one, one_sq, st1 = d.render_multi([0], spp=6, seed=13, splits=1, sumsq=True)
+    assert np.array_equal(one, ref) and np.array_equal(one_sq, ref_sq) and st1["rays"] == st["rays"] and st1["samples"] == st["samples"]
+    with pytest.raises(LumillyError):
+        d.render_multi([0, 0], spp=2)
+    with pytest.raises(LumillyError):
+        d.render_multi([0, 99], spp=2)
+    with pytest.raises(LumillyError):
+        d.render_multi([], spp=2)
+    # the library is still usable on device 0 afterwards
+    again, _, _ = s.render(spp=6, seed=13, splits=1)
+    assert np.array_equal(again, ref)
+    if torch.cuda.device_count() < 2:
+        pytest.skip("the two-device half needs 2 GPUs (gpurun --gpus 2)")
+    two, two_sq, st2 = d.render_multi([0, 1], spp=6, seed=13, splits=1, sumsq=True)
+    rep, _, _ = d.render_multi([0, 1], spp=6, seed=13, splits=1)
+    assert np.array_equal(two, rep)
+    assert st2["rays"] == st["rays"] and st2["samples"] == st["samples"] and st2["nonfinite_samples"] == st["nonfinite_samples"]
+    assert np.allclose(two, ref, rtol=1e-5, atol=1e-6) and np.allclose(two_sq, ref_sq, rtol=1e-5, atol=1e-6)
+    # the ranges are the ones a 2-rank run renders: [0, 3) and [3, 6)
+    lo, _, _ = s.render(spp=3, spp_begin=0, seed=13, splits=1)
+    hi, _, _ = s.render(spp=3, spp_begin=3, seed=13, splits=1)
+    assert np.allclose(two, (lo + hi) / 2, rtol=1e-6, atol=1e-7)
+    # more devices than samples: the idle device contributes zeros
+    few, _, stf = d.render_multi([1, 0], spp=1, seed=13, splits=1)
+    solo, _, sts = s.render(spp=1, seed=13, splits=1)
+    assert np.array_equal(few, solo) and stf["rays"] == sts["rays"]
+
+
 def test_error_paths(scenes, lr):
     from lumillyrender_b200.capi import LumillyError
     d, s, o = scenes("primitive")

@@ -494,13 +494,26 @@ int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_
     sum_src.count = sq_src.count = n_devices;
     size_t staged_floats = 0;
     std::vector<int> mapped(n_devices, 1);
+    const bool no_peer = std::getenv("LR_MULTI_NO_PEER") != nullptr;      // development / tests: force the staged path
     for (int i = 1; i < n_devices && e == cudaSuccess; i++) {
       int can = 0;
-      cudaDeviceCanAccessPeer(&can, devices[0], devices[i]);
+      if (!no_peer) cudaDeviceCanAccessPeer(&can, devices[0], devices[i]);
       if (can) {
+        // the film buffers come from device i's stream-ordered pool: the pool must grant devices[0] access (plain
+        // cudaDeviceEnablePeerAccess covers cudaMalloc memory only)
         const cudaError_t pe = cudaDeviceEnablePeerAccess(devices[i], 0);
         if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
         else if (pe != cudaSuccess) { can = 0; cudaGetLastError(); }
+        cudaMemPool_t pool;
+        cudaMemAccessDesc ad;
+        std::memset(&ad, 0, sizeof(ad));
+        ad.location.type = cudaMemLocationTypeDevice;
+        ad.location.id = devices[0];
+        ad.flags = cudaMemAccessFlagsProtReadWrite;
+        if (can && (cudaDeviceGetDefaultMemPool(&pool, devices[i]) != cudaSuccess || cudaMemPoolSetAccess(pool, &ad, 1) != cudaSuccess)) {
+          can = 0;
+          cudaGetLastError();
+        }
       }
       mapped[i] = can;
       if (!can) staged_floats += n * (out_sumsq ? 2 : 1);

@@ -244,7 +244,7 @@ def test_pool_kernel_small_work(scenes):
     assert np.allclose((lo * 2 + hi) / 3, full, rtol=1e-5, atol=1e-6)
 
 
-def test_render_multi_single_process(scenes, lr, gpu):
+def test_render_multi_single_process(scenes, lr, gpu, monkeypatch):
     """lr_render_multi (one process, the scene on every listed device, sample ranges sharded, one peer-reading reduce
     kernel): with one device it is lr_render bit for bit; with two it equals the single-device render up to the fp32
     order of the cross-device sum, ray counts add up exactly, and it is reproducible.  Error paths return codes."""
@@ -268,6 +268,10 @@ def test_render_multi_single_process(scenes, lr, gpu):
     two, two_sq, st2 = d.render_multi([0, 1], spp=6, seed=13, splits=1, sumsq=True)
     rep, _, _ = d.render_multi([0, 1], spp=6, seed=13, splits=1)
     assert np.array_equal(two, rep)
+    monkeypatch.setenv("LR_MULTI_NO_PEER", "1")                  # the staged-copy path where a peer cannot be mapped
+    staged, staged_sq, _ = d.render_multi([0, 1], spp=6, seed=13, splits=1, sumsq=True)
+    monkeypatch.delenv("LR_MULTI_NO_PEER")
+    assert np.array_equal(staged, two) and np.array_equal(staged_sq, two_sq)
     assert st2["rays"] == st["rays"] and st2["samples"] == st["samples"] and st2["nonfinite_samples"] == st["nonfinite_samples"]
     assert np.allclose(two, ref, rtol=1e-5, atol=1e-6) and np.allclose(two_sq, ref_sq, rtol=1e-5, atol=1e-6)
     # the ranges are the ones a 2-rank run renders: [0, 3) and [3, 6)

@@ -61,6 +61,7 @@ struct LrScene {
   DevScene dev{};
   std::vector<void*> allocs;
   uint64_t h2d_bytes = 0;
+  size_t block_bytes = 0;                          // size of the one device block (scene arrays + counter words)
   int width = 0, height = 0;
   unsigned long long* d_counters = nullptr;
   // scratch (mutable: owned by the handle, one caller thread at a time per LrScene)
@@ -233,6 +234,7 @@ int lr_scene_create(const LrSceneDesc* d, LrScene** out) {
       e = dev_alloc((void**)&block, total);
       if (e == cudaSuccess) {
         s->allocs.push_back(block);
+        s->block_bytes = total;
         if (upload_bytes > 0) e = cudaMemcpyAsync(block, h, upload_bytes, cudaMemcpyHostToDevice, 0);
         if (e == cudaSuccess) e = cudaMemsetAsync(block + o_counters, 0, C_COUNT * sizeof(unsigned long long), 0);
         if (e == cudaSuccess) e = cudaStreamSynchronize(0);             // the arena is reused by the next call
@@ -437,6 +439,44 @@ int lr_render(const LrScene* s, const LrRenderParams* p, float* out_rgb, float* 
   return rc;
 }
 
+// A copy of a device scene on the CURRENT device: the packed block travels device to device (NVLink) instead of being
+// packed and uploaded from the host again, and the array pointers are rebased into the new block.
+static int scene_clone(const LrScene* src, int src_device, int dst_device, LrScene** out) {
+  *out = nullptr;
+  if (src->allocs.size() != 1 || src->block_bytes == 0) return fail(LR_ERR_INVALID, "scene_clone: unexpected scene layout");
+  LrScene* s = new LrScene();
+  char* block = nullptr;
+  const char* from = (const char*)src->allocs[0];
+  cudaError_t e = dev_alloc((void**)&block, src->block_bytes);
+  if (e == cudaSuccess) {
+    s->allocs.push_back(block);
+    s->block_bytes = src->block_bytes;
+    e = cudaMemcpyPeerAsync(block, dst_device, from, src_device, src->h2d_bytes, 0);
+  }
+  const size_t o_counters = (const char*)src->d_counters - from;
+  if (e == cudaSuccess) e = cudaMemsetAsync(block + o_counters, 0, C_COUNT * sizeof(unsigned long long), 0);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev0, cudaEventDefault);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev1, cudaEventDefault);
+  if (e != cudaSuccess) {
+    const std::string msg = std::string("scene clone: ") + cudaGetErrorString(e);
+    lr_scene_destroy(s);
+    return fail(LR_ERR_CUDA, msg);
+  }
+  s->dev = src->dev;
+  auto rebase = [&](const void* p) -> const void* { return p ? (const void*)(block + ((const char*)p - from)) : nullptr; };
+  s->dev.nodes = (const float4*)rebase(src->dev.nodes); s->dev.tris = (const float4*)rebase(src->dev.tris);
+  s->dev.tri_n = (const float4*)rebase(src->dev.tri_n); s->dev.tri_box = (const float4*)rebase(src->dev.tri_box);
+  s->dev.spheres = (const float4*)rebase(src->dev.spheres); s->dev.sphere_meta = (const int2*)rebase(src->dev.sphere_meta);
+  s->dev.mats = (const float4*)rebase(src->dev.mats);
+  s->dev.emitter_cdf = (const float*)rebase(src->dev.emitter_cdf); s->dev.emitters = (const float4*)rebase(src->dev.emitters);
+  s->dev.sky_pixels = (const float4*)rebase(src->dev.sky_pixels);
+  s->d_counters = (unsigned long long*)(block + o_counters);
+  s->h2d_bytes = src->h2d_bytes;
+  s->width = src->width; s->height = src->height; s->has_ggx = src->has_ggx;
+  *out = s;
+  return LR_OK;
+}
+
 int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_devices, const int32_t* devices, float* out_rgb,
                     float* out_sumsq, LrStats* stats) {
   if (!desc || !p || !devices || !out_rgb) return fail(LR_ERR_INVALID, "null argument");
@@ -462,11 +502,13 @@ int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_
   LrStats total;
   std::memset(&total, 0, sizeof(total));
   do {
-    // ---- upload and launch: every call below is asynchronous, so the devices render concurrently
+    // ---- scenes first: the first device gets the scene from the host, the others a device-to-device copy of its packed
+    // block.  (A peer copy in the default stream waits for the work queued on BOTH devices, so no render may be running
+    // yet: with the copies interleaved between the launches the devices rendered one after the other.)
     const int per = p->spp_count / n_devices, rem = p->spp_count % n_devices;
     for (int i = 0; i < n_devices && rc == LR_OK; i++) {
       if ((rc = lr_init(devices[i])) != LR_OK) break;      // cudaSetDevice + the non-trimming memory pool
-      if ((rc = lr_scene_create(desc, &scenes[i])) != LR_OK) break;
+      if ((rc = i == 0 ? lr_scene_create(desc, &scenes[0]) : scene_clone(scenes[0], devices[0], devices[i], &scenes[i])) != LR_OK) break;
       const LrScene* s = scenes[i];
       parts[i].spp_begin = p->spp_begin + i * per + std::min(i, rem);
       parts[i].spp_count = per + (i < rem ? 1 : 0);
@@ -479,7 +521,14 @@ int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_
       if (out_sumsq && (rc = ensure_scratch(&s->d_film_sq, &s->film_sq_floats, n)) != LR_OK) break;
       cudaError_t e = cudaMemsetAsync(s->d_film, 0, n * sizeof(float), 0);
       if (e == cudaSuccess && out_sumsq) e = cudaMemsetAsync(s->d_film_sq, 0, n * sizeof(float), 0);
-      if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("cudaMemsetAsync: ") + cudaGetErrorString(e)); break; }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(0);  // the copy has landed before anything is launched anywhere
+      if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("lr_render_multi set-up: ") + cudaGetErrorString(e)); break; }
+    }
+    // ---- launch: asynchronous, so the devices render concurrently
+    for (int i = 0; i < n_devices && rc == LR_OK; i++) {
+      cudaError_t e = cudaSetDevice(devices[i]);
+      if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); break; }
+      const LrScene* s = scenes[i];
       if (parts[i].spp_count > 0 &&
           (rc = lr_render_accumulate_device(s, &parts[i], s->d_film, out_sumsq ? s->d_film_sq : nullptr, nullptr)) != LR_OK) break;
       e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);

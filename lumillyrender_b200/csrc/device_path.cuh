@@ -223,16 +223,14 @@ LR_DEV bool bvh_bounds_hit(const DevScene& sc, F3 o, F3 inv, float cull_t) {
   return en <= ex;
 }
 
-// BVH part of the nearest-hit query: "while-while" traversal (every lane first descends inner nodes until it holds
-// a leaf or is done, the warp reconverges, then the lanes that hold leaves test triangles together), near child
-// first, per-thread stack, nodes culled against [0, cull_t] on host-padded boxes.  best_t / best come in holding the
-// nearest flat candidate (or 3e38 / -1) and are replaced only by something strictly nearer.
-//   STRICT = true : a candidate must also pass the reference's gate on the triangle's own AABB (bvh.rs:21-25)
-//                   when it becomes the nearest — the reference's semantics, candidate by candidate.
-//   STRICT = false: optimistic accept; the caller gates the final nearest hit once (bvh_hit_is_gated) and falls back
-//                   to the strict query if it fails.  If the nearest candidate passes, it IS the gated nearest hit
-//                   (the minimum over a superset that lies in the subset).
-template <bool COUNT, bool STRICT>
+// BVH part of the STRICT nearest-hit query (probes, and the re-trace of the rare ray whose optimistic hit fails the gate):
+// "while-while" traversal (every lane first descends inner nodes until it holds a leaf or is done, the warp
+// reconverges, then the lanes that hold leaves test triangles together), near child first, per-thread stack, nodes
+// culled against [0, cull_t] on host-padded boxes.  best_t / best come in holding the nearest flat candidate (or
+// 3e38 / -1) and are replaced only by something strictly nearer that also passes the reference's gate on the
+// triangle's own AABB (bvh.rs:21-25) — the reference's semantics, candidate by candidate.  The render kernels use the
+// optimistic form below (trav_step: accept on the primitive test alone, gate the final nearest hit once).
+template <bool COUNT>
 LR_DEV void bvh_traverse(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, int& best, TraceCounters& tc) {
   // conservative cull distance: a primitive's computed t may precede its box's computed entry
   float cull_t = best_t < 3.0e38f ? best_t * 1.0001f + 1e-4f : 3.0e38f;
@@ -281,8 +279,8 @@ LR_DEV void bvh_traverse(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, 
         if (COUNT) tc.tris++;
         const float t = triangle_mt(f3(v0), f3(v1), f3(v2), o, d);
         if (t >= 0.0f && t < best_t) {
-          // STRICT: the leaf's own AABB gate (triangle.rs:102-119 box, aabb.rs:75-92 test)
-          if (!STRICT || tri_gate(sc, o, inv, first + k)) {
+          // the leaf's own AABB gate (triangle.rs:102-119 box, aabb.rs:75-92 test)
+          if (tri_gate(sc, o, inv, first + k)) {
             best_t = t;
             best = first + k;
             cull_t = best_t * 1.0001f + 1e-4f;
@@ -294,7 +292,9 @@ LR_DEV void bvh_traverse(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, 
   }
 }
 
-// The same query as bvh_traverse<COUNT, false>, organised as ONE loop whose every iteration advances a lane by at most
+// The optimistic form of the same query (accept on the primitive test, the caller gates the final nearest hit once with
+// bvh_hit_is_gated and falls back to the strict query if it fails: if the nearest candidate passes, it IS the gated nearest
+// hit — the minimum over a superset that lies in the subset), organised as ONE loop whose every iteration advances a lane by at most
 // one inner node AND at most one triangle test: a leaf the descent reaches is moved to a one-entry leaf slot and the
 // descent goes on with the next stack entry while the slot's (<= 8) triangles are tested one per iteration.  In the
 // while-while form the lanes of a warp wait at the leaf step for the lane with the longest run of inner nodes (ncu:
@@ -389,7 +389,7 @@ LR_DEV void trace(const DevScene& sc, F3 o, F3 d, float& t_out, int& id_out, Tra
   float best_t = 3.0e38f;
   int best = -1;
   flat_hits<COUNT>(sc, o, d, inv, best_t, best, tc);
-  if (sc.n_nodes > 0) bvh_traverse<COUNT, true>(sc, o, d, inv, best_t, best, tc);
+  if (sc.n_nodes > 0) bvh_traverse<COUNT>(sc, o, d, inv, best_t, best, tc);
   t_out = best_t;
   id_out = best;
 }

@@ -47,6 +47,11 @@ extern "C" {
     pub fn lr_render(scene: *const LrScene, params: *const LrRenderParams, out_rgb: *mut f32, out_sumsq: *mut f32, stats: *mut LrStats) -> c_int;
     pub fn lr_render_accumulate_device(scene: *const LrScene, params: *const LrRenderParams, d_sum: *mut f32, d_sumsq: *mut f32, stream: *mut c_void) -> c_int;
     pub fn lr_stats_fetch(scene: *const LrScene, stream: *mut c_void, stats: *mut LrStats) -> c_int;
+    pub fn lr_shard_range(spp_begin: i32, spp_count: i32, part: i32, n_parts: i32, begin: *mut i32, count: *mut i32) -> c_int;
+    /// main.rs:70-132 on several GPUs of one box from this one process (scene on every device, sample ranges sharded,
+    /// one peer-reading reduce kernel on devices[0])
+    pub fn lr_render_multi(desc: *const LrSceneDesc, params: *const LrRenderParams, n_devices: i32, devices: *const i32,
+                           out_rgb: *mut f32, out_sumsq: *mut f32, stats: *mut LrStats) -> c_int;
     pub fn lr_trace_primary(scene: *const LrScene, u: f32, v: f32, ua: f32, va: f32, prim: *mut i32, t: *mut f32) -> c_int;
     pub fn lr_host_scene_load(toml_path: *const c_char, asset_root: *const c_char, w: i32, h: i32, out: *mut *mut LrHostScene) -> c_int;
     pub fn lr_host_scene_from_arrays(materials: *const LrMaterial, n_materials: i32, triangles: *const LrTriangle, n_triangles: i32,

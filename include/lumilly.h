@@ -210,6 +210,11 @@ int lr_stats_fetch(const LrScene* scene, void* cuda_stream, LrStats* stats);
    spp_count.  out_rgb / out_sumsq / stats as lr_render (stats are totals, kernel_ms the slowest device's).
    1 <= n_devices <= 8, device ids distinct.  The result for a given device COUNT is bit-reproducible and
    differs from other counts only by fp32 summation order. */
+/* The sample-range sharding rule, for any host that shards by itself (one process per GPU): part `part` of
+   `n_parts` of the range [spp_begin, spp_begin + spp_count) — consecutive ranges that tile it exactly, sizes
+   differing by <= 1, the larger ones first.  lr_render_multi and bench.py's ranks use this rule. */
+int lr_shard_range(int32_t spp_begin, int32_t spp_count, int32_t part, int32_t n_parts, int32_t* begin, int32_t* count);
+
 int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* params, int32_t n_devices, const int32_t* devices,
                     float* out_rgb, float* out_sumsq, LrStats* stats);
 

@@ -96,6 +96,7 @@ SIGNATURES = {
     "lr_render": (C.c_int, [_VP, C.POINTER(LrRenderParams), _PF, _PF, C.POINTER(LrStats)]),
     "lr_render_accumulate_device": (C.c_int, [_VP, C.POINTER(LrRenderParams), _VP, _VP, _VP]),
     "lr_stats_fetch": (C.c_int, [_VP, _VP, C.POINTER(LrStats)]),
+    "lr_shard_range": (C.c_int, [i32, i32, i32, i32, _PI, _PI]),
     "lr_render_multi": (C.c_int, [C.POINTER(LrSceneDesc), C.POINTER(LrRenderParams), i32, _PI, _PF, _PF, C.POINTER(LrStats)]),
     "lr_trace_primary": (C.c_int, [_VP, f32, f32, f32, f32, _PI, _PF]),
     "lr_trace_rays": (C.c_int, [_VP, i64, _PF, _PF, _PI, _PF, _PF]),

@@ -439,6 +439,15 @@ int lr_render(const LrScene* s, const LrRenderParams* p, float* out_rgb, float* 
   return rc;
 }
 
+int lr_shard_range(int32_t spp_begin, int32_t spp_count, int32_t part, int32_t n_parts, int32_t* begin, int32_t* count) {
+  if (!begin || !count) return fail(LR_ERR_INVALID, "null argument");
+  if (n_parts <= 0 || part < 0 || part >= n_parts || spp_count < 0 || spp_begin < 0) return fail(LR_ERR_INVALID, "bad shard request");
+  const int per = spp_count / n_parts, rem = spp_count % n_parts;
+  *begin = spp_begin + part * per + std::min(part, rem);
+  *count = per + (part < rem ? 1 : 0);
+  return LR_OK;
+}
+
 // A copy of a device scene on the CURRENT device: the packed block travels device to device (NVLink) instead of being
 // packed and uploaded from the host again, and the array pointers are rebased into the new block.
 static int scene_clone(const LrScene* src, int src_device, int dst_device, LrScene** out) {
@@ -505,13 +514,11 @@ int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_
     // ---- scenes first: the first device gets the scene from the host, the others a device-to-device copy of its packed
     // block.  (A peer copy in the default stream waits for the work queued on BOTH devices, so no render may be running
     // yet: with the copies interleaved between the launches the devices rendered one after the other.)
-    const int per = p->spp_count / n_devices, rem = p->spp_count % n_devices;
     for (int i = 0; i < n_devices && rc == LR_OK; i++) {
       if ((rc = lr_init(devices[i])) != LR_OK) break;      // cudaSetDevice + the non-trimming memory pool
       if ((rc = i == 0 ? lr_scene_create(desc, &scenes[0]) : scene_clone(scenes[0], devices[0], devices[i], &scenes[i])) != LR_OK) break;
       const LrScene* s = scenes[i];
-      parts[i].spp_begin = p->spp_begin + i * per + std::min(i, rem);
-      parts[i].spp_count = per + (i < rem ? 1 : 0);
+      if ((rc = lr_shard_range(p->spp_begin, p->spp_count, i, n_devices, &parts[i].spp_begin, &parts[i].spp_count)) != LR_OK) break;
       DevParams dp;
       LrRenderParams probe = parts[i];
       if (probe.spp_count == 0) probe.spp_count = 1;       // more devices than samples: this one only contributes zeros

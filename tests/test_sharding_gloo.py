@@ -23,6 +23,27 @@ def test_shard_ranges_tile_exactly():
         shard_range(8, 2, 2)
 
 
+def test_c_abi_shard_rule_is_the_python_one(lr):
+    """lr_shard_range (what lr_render_multi and a Rust / C++ host use) and distributed.shard_range (what bench.py's ranks
+    use) are the same rule; bad requests are errors, not ranges.  No GPU needed."""
+    import ctypes as C
+    from lumillyrender_b200 import capi
+    from lumillyrender_b200.distributed import shard_range
+    lib = capi.load_library()
+    for begin in (0, 5):
+        for total in (0, 1, 7, 64, 1000):
+            for world in (1, 2, 3, 8):
+                for r in range(world):
+                    b, c = C.c_int32(-1), C.c_int32(-1)
+                    assert lib.lr_shard_range(begin, total, r, world, C.byref(b), C.byref(c)) == 0
+                    lo, hi = shard_range(total, r, world)
+                    assert (b.value, c.value) == (begin + lo, hi - lo)
+    b, c = C.c_int32(), C.c_int32()
+    for bad in ((0, 8, 2, 2), (0, 8, -1, 2), (0, 8, 0, 0), (0, -1, 0, 1), (-1, 8, 0, 1)):
+        assert lib.lr_shard_range(*bad, C.byref(b), C.byref(c)) != 0
+    assert lib.lr_shard_range(0, 8, 0, 1, None, C.byref(c)) != 0
+
+
 def _worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -501,6 +502,15 @@ int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_
   int prev_device = 0;
   cudaGetDevice(&prev_device);
   const int home = g_device >= 0 ? g_device : devices[0];
+  // LR_MULTI_TRACE=1: wall-clock milliseconds of each phase on stderr (development)
+  const bool trace_on = std::getenv("LR_MULTI_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace_on) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "lr_render_multi %-8s %8.2f ms\n", what, std::chrono::duration<float, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
 
   std::vector<LrScene*> scenes(n_devices, nullptr);
   std::vector<LrRenderParams> parts(n_devices, *p);
@@ -531,6 +541,7 @@ int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_
       if (e == cudaSuccess) e = cudaStreamSynchronize(0);  // the copy has landed before anything is launched anywhere
       if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("lr_render_multi set-up: ") + cudaGetErrorString(e)); break; }
     }
+    lap("set-up");
     // ---- launch: asynchronous, so the devices render concurrently
     for (int i = 0; i < n_devices && rc == LR_OK; i++) {
       cudaError_t e = cudaSetDevice(devices[i]);
@@ -543,6 +554,7 @@ int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_
       if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("cudaEventRecord: ") + cudaGetErrorString(e)); break; }
     }
     if (rc != LR_OK) break;
+    lap("launch");
 
     // ---- reduce + normalise on devices[0]
     cudaError_t e = cudaSetDevice(devices[0]);
@@ -551,6 +563,7 @@ int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_
     size_t staged_floats = 0;
     std::vector<int> mapped(n_devices, 1);
     const bool no_peer = std::getenv("LR_MULTI_NO_PEER") != nullptr;      // development / tests: force the staged path
+    static bool pool_mapped[64][64] = {};                                // [reader][owner]: the owner's pool already grants the reader access
     for (int i = 1; i < n_devices && e == cudaSuccess; i++) {
       int can = 0;
       if (!no_peer) cudaDeviceCanAccessPeer(&can, devices[0], devices[i]);
@@ -566,9 +579,14 @@ int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_
         ad.location.type = cudaMemLocationTypeDevice;
         ad.location.id = devices[0];
         ad.flags = cudaMemAccessFlagsProtReadWrite;
-        if (can && (cudaDeviceGetDefaultMemPool(&pool, devices[i]) != cudaSuccess || cudaMemPoolSetAccess(pool, &ad, 1) != cudaSuccess)) {
-          can = 0;
-          cudaGetLastError();
+        const bool known = devices[0] < 64 && devices[i] < 64 && pool_mapped[devices[0]][devices[i]];
+        if (can && !known) {
+          if (cudaDeviceGetDefaultMemPool(&pool, devices[i]) != cudaSuccess || cudaMemPoolSetAccess(pool, &ad, 1) != cudaSuccess) {
+            can = 0;
+            cudaGetLastError();
+          } else if (devices[0] < 64 && devices[i] < 64) {
+            pool_mapped[devices[0]][devices[i]] = true;
+          }
         }
       }
       mapped[i] = can;
@@ -590,12 +608,14 @@ int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_
         }
       }
     }
+    lap("peers");
     if (e == cudaSuccess) e = launch_reduce_peers(scenes[0]->d_film, sum_src, n, (float)p->spp_count, 0);   // main.rs:104
     if (e == cudaSuccess && out_sumsq) e = launch_reduce_peers(scenes[0]->d_film_sq, sq_src, n, 0.0f, 0);
     if (e == cudaSuccess) e = cudaMemcpy(out_rgb, scenes[0]->d_film, n * sizeof(float), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && out_sumsq) e = cudaMemcpy(out_sumsq, scenes[0]->d_film_sq, n * sizeof(float), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("lr_render_multi reduce: ") + cudaGetErrorString(e)); break; }
 
+    lap("render+d2h");
     // ---- statistics: totals over the devices, the slowest device's kernel time
     for (int i = 0; i < n_devices && rc == LR_OK; i++) {
       if (cudaSetDevice(devices[i]) != cudaSuccess) { rc = fail(LR_ERR_CUDA, "cudaSetDevice failed"); break; }
@@ -621,6 +641,7 @@ int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_
   }
   cudaSetDevice(home >= 0 && home < n_visible ? home : prev_device);
   g_device = home;
+  lap("clean-up");
   if (rc != LR_OK) { g_error = err; return rc; }
   if (stats) *stats = total;
   return LR_OK;

@@ -16,7 +16,7 @@ fn main() {
         .status()
         .expect("python3 not found: lumilly-sys builds through lumillyrender_b200/build.py");
     assert!(status.success(), "lumillyrender_b200/build.py failed (nvcc missing? there is no CPU fallback)");
-    for f in ["build.py", "csrc/kernels.cu", "csrc/api.cpp", "csrc/persistent_inst.cu", "csrc/persistent.cuh", "csrc/pool.cuh",
+    for f in ["build.py", "csrc/kernels.cu", "csrc/api.cpp", "csrc/persistent_inst.cu", "csrc/persistent.cuh", "csrc/pool.cuh", "csrc/path_vertex.inc",
               "csrc/device_path.cuh", "csrc/device_scene.h", "csrc/bvh_build.cpp", "csrc/toml_obj.cpp", "csrc/host_scene.cpp",
               "csrc/image_io.cpp"].iter() {
         println!("cargo:rerun-if-changed={}", pkg.join(f).display());

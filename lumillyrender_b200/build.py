@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblumilly_b200.so")
 CLI = os.path.join(HERE, "bin", "lumilly")
 SOURCES = ["kernels.cu", "api.cpp", "bvh_build.cpp", "toml_obj.cpp", "host_scene.cpp", "image_io.cpp"]
-HEADERS = ["device_scene.h", "device_path.cuh", "persistent.cuh", "pool.cuh", "kernels.h", "common.h", "host_scene.h", "../../include/lumilly.h"]
+HEADERS = ["device_scene.h", "device_path.cuh", "persistent.cuh", "pool.cuh", "path_vertex.inc", "kernels.h", "common.h", "host_scene.h", "../../include/lumilly.h"]
 
 
 def _nvcc():

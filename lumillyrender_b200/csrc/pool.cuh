@@ -187,206 +187,8 @@ render_pool_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ 
         if (want_sumsq) sumsq = f3(SLF(W_SQ), SLF(W_SQ + 1), SLF(W_SQ + 2));
       }
 
-      bool need_new = false;
-      bool fetch_unit = false;
-      if (ready) {
-        if (flags & F_HAS_RAY) {
-          int depth = flags & F_DEPTH_MASK;
-          bool allow_emission = (flags & F_ALLOW_EMISSION) != 0;
-          bool has_shadow_next = false;
-          const F3 d = d0;
-          if (NR == 2 && (flags & F_HAS_SHADOW)) {
-            // visibility + contribution of the shadow ray issued at the previous vertex: scene.rs:127-150
-            if (id1 != -1 && fabsf(t1 - q_dist) <= kEPS) {
-              const Surface lf = surface_at(sc, o, d1, t1, id1);  // o = the vertex position = both rays' origin
-              const float light_cos = dot(-d1, lf.n);
-              if (light_cos > 0.0f) {
-                const Mat lm = load_mat(sc, lf.mat);
-                const float g_term = q_point_cos * light_cos / q_sqr;
-                const F3 l_i = lm.emissive ? lm.emission : f3(0.0f, 0.0f, 0.0f);
-                const F3 direct = q_brdf * l_i * g_term / q_pdf;
-                // scene.rs:192 (T of the vertex, before its BSDF update); x / 1.0f == x exactly, the usual p_rr
-                L = L + q_T * (q_prr != 1.0f ? direct / q_prr : direct);
-              }
-            }
-          }
-          bool finish = false;
-          if (id0 == -1) {
-            L = L + T * sky_radiance(sc, d);                // scene.rs:29 / 43
-            finish = true;
-          } else {
-            const float t = t0;
-            const Surface sf = surface_at(sc, o, d, t, id0);
-            const Mat m = load_mat(sc, sf.mat);
-            const F3 wo = -d;
-            // emission: scene.rs:155-159 / 175-179
-            if (!(p.no_direct_emitter && depth == 0) && allow_emission && dot(wo, sf.n) > 0.0f && m.emissive)
-              L = L + T * m.emission;
-            // Russian roulette: scene.rs:64-76, 161-164
-            float prr = m.weight;
-            if (depth > p.depth_limit) prr *= scalbnf(1.0f, -(depth - p.depth_limit));
-            if (depth <= p.depth && prr > 0.0f) prr = 1.0f;
-            if (prr != 1.0f && rng.next() >= prr) {
-              finish = true;
-            } else {
-              F3 nee_dir = f3(0, 0, 1), pn = sf.n;
-              if (NR == 2) {
-                allow_emission = false;                          // every deeper vertex: no_emission = true (scene.rs:189)
-                // direct_light_radiance: scene.rs:104-125
-                if (!m.emissive && sc.n_emitters > 0) {
-                  // Objects::sample_emission objects.rs:37-51 (prefix-sum CDF, first i with roulette <= cdf[i])
-                  const float roulette = sc.emission_area * rng.next();
-                  int lo = 0, hi = sc.n_emitters - 1;
-                  while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (roulette <= __ldg(sc.emitter_cdf + mid)) hi = mid; else lo = mid + 1;
-                  }
-                  const float4 e0 = ldg4(sc.emitters + 3 * lo), e1 = ldg4(sc.emitters + 3 * lo + 1), e2 = ldg4(sc.emitters + 3 * lo + 2);
-                  const float u1 = rng.next();
-                  const float u2 = rng.next();
-                  F3 q;
-                  const float area = e1.w;
-                  if (__float_as_int(e0.w) == 0) {               // Triangle::sample triangle.rs:140-149
-                    const float mn = fminf(u1, u2), mx = fmaxf(u1, u2);
-                    q = f3(e0) * mn + f3(e1) * (1.0f - mx) + f3(e2) * (mx - mn);
-                  } else {                                       // Sphere::sample sphere.rs:79-84 + util.rs:108-116
-                    const float r1 = 2.0f * kPI * u1;
-                    const float r2 = u2 * 2.0f - 1.0f;
-                    const float r2s = sqrtf(1.0f - r2 * r2);
-                    float sn, cs;
-                    spec_sincos(r1, &sn, &cs);
-                    q = f3(e0) + e1.x * f3(cs * r2s, sn * r2s, r2);
-                  }
-                  const F3 direct_path = q - sf.pos;
-                  nee_dir = normalize(direct_path);
-                  pn = orienting_normal(wo, sf.n);
-                  if (dot(nee_dir, pn) > 0.0f) {
-                    // the shadow ray travels with the extension ray; what its resolve needs is kept
-                    q_T = T; q_prr = prr;
-                    q_point_cos = dot(nee_dir, pn);
-                    q_dist = norm(direct_path); q_sqr = sqr_norm(direct_path);
-                    q_pdf = (1.0f / area) * area / sc.emission_area;
-                    has_shadow_next = true;
-                  }
-                }
-              }
-              // material_interaction_radiance: scene.rs:78-102 (the draws come after the NEE draws, as in scene.rs:186-190)
-              F3 wi;
-              float pdf;
-              mat_sample(m, wo, sf.n, rng, wi, pdf);
-              // Material::brdf for the shadow direction (oriented normal, scene.rs:141) and for the sampled one
-              // (scene.rs:88) through ONE call site
-              F3 f_bsdf = f3(0, 0, 0);
-#pragma unroll 1
-              for (int k = (NR == 2 && has_shadow_next) ? 0 : 1; k < 2; k++) {
-                const F3 f = mat_brdf(m, wo, k == 0 ? nee_dir : wi, k == 0 ? pn : sf.n, sf.pos);
-                if (k == 0) q_brdf = f; else f_bsdf = f;
-              }
-              const F3 coef = mat_coef(m, wo, sf.n, t);
-              const float c = dot(wi, sf.n);                     // UNoriented normal (scene.rs:91)
-              T = T * (f_bsdf * coef * c / pdf);
-              if (prr != 1.0f) T = T / prr;                      // x / 1.0f == x exactly: the common case skips 3 divisions
-              o = sf.pos;                                        // no origin offset (scene.rs:94-97)
-              d0 = wi;
-              if (NR == 2 && has_shadow_next) d1 = nee_dir;
-              depth++;
-            }
-          }
-          if (finish) {
-            // main.rs:99-102
-            const F3 e = (L * cam_g) * cam_w;
-            if (!(isfinite(e.x) && isfinite(e.y) && isfinite(e.z))) n_nonfinite++;
-            sum = sum + e;
-            if (want_sumsq) sumsq = sumsq + e * e;
-            un.y += 1;
-            need_new = true;
-          }
-          flags = (flags & ~(F_DEPTH_MASK | F_ALLOW_EMISSION | F_HAS_SHADOW)) | (depth & F_DEPTH_MASK) |
-                  (allow_emission ? F_ALLOW_EMISSION : 0) | (has_shadow_next ? F_HAS_SHADOW : 0);
-        } else {
-          need_new = true;                                       // fresh slot
-        }
-
-        // ---- the unit's sample range is done: write its sums and ask for the next unit
-        if (need_new && (!(flags & F_HAS_UNIT) || un.y >= un.z)) {
-          if (flags & F_HAS_UNIT) {
-            const size_t pi = (size_t)un.x, n_px = (size_t)p.crop_w * p.crop_h;
-            if (p.splits == 1) {
-              out_sum[3 * pi + 0] += sum.x; out_sum[3 * pi + 1] += sum.y; out_sum[3 * pi + 2] += sum.z;
-              if (want_sumsq) { out_sumsq[3 * pi + 0] += sumsq.x; out_sumsq[3 * pi + 1] += sumsq.y; out_sumsq[3 * pi + 2] += sumsq.z; }
-            } else {
-              // per-split partial buffers, reduced in split order by reduce_splits_kernel (deterministic)
-              float* ps = out_sum + 3 * (n_px * un.w + pi);
-              ps[0] = sum.x; ps[1] = sum.y; ps[2] = sum.z;
-              if (want_sumsq) { float* pq = out_sumsq + 3 * (n_px * un.w + pi); pq[0] = sumsq.x; pq[1] = sumsq.y; pq[2] = sumsq.z; }
-            }
-          }
-          fetch_unit = true;
-        }
-      }
-
-      // ---- warp-aggregated unit fetch (slots that ask together receive consecutive units = pixels of one 8x4 tile)
-      {
-        bool need = fetch_unit;
-        while (true) {
-          const unsigned m = __ballot_sync(kFull, need);
-          if (m == 0u) break;
-          const int leader = __ffs(m) - 1;
-          unsigned int base = 0;
-          if (lane == leader) base = atomicAdd(next_unit, (unsigned int)__popc(m));
-          base = __shfl_sync(kFull, base, leader);
-          if (need) {
-            const unsigned int u = base + (unsigned int)__popc(m & lanemask_lt());
-            if (u >= n_units) {
-              alive = false;
-              need = false;
-            } else {
-              int lx, ly, split;
-              if (decode_unit(p, u, lx, ly, split)) {
-                const int per = p.spp_count / p.splits, rem = p.spp_count % p.splits;
-                un.x = ly * p.crop_w + lx;
-                un.y = p.spp_begin + split * per + min(split, rem);
-                un.z = un.y + per + (split < rem ? 1 : 0);
-                un.w = split;
-                flags |= F_HAS_UNIT;
-                sum = f3(0.0f, 0.0f, 0.0f);
-                sumsq = f3(0.0f, 0.0f, 0.0f);
-                need = false;
-              }
-            }
-          }
-        }
-      }
-
-      const bool go = ready && alive;
-      if (go && need_new) {
-        // next sample of the slot's pixel: camera ray (camera.rs), fresh path state
-        const int lx = un.x % p.crop_w, ly = un.x / p.crop_w;
-        const int x = p.crop_x + lx, y = p.crop_y + ly;
-        const unsigned int pixel = (unsigned int)(y * sc.cam.width + x);
-        rng.seed(p.seed, pixel, (unsigned int)un.y);
-        camera_sample_rng(sc.cam, x, y, rng, o, d0, cam_g, cam_w);
-        T = f3(1.0f, 1.0f, 1.0f);
-        L = f3(0.0f, 0.0f, 0.0f);
-        flags = (flags & ~(F_DEPTH_MASK | F_HAS_SHADOW)) | F_ALLOW_EMISSION | F_HAS_RAY;
-      }
-      // ---- inline part of Objects::intersect (objects.rs:63-65) for the new ray(s), one call site: the candidates
-      // every ray tests, then whether the ray can reach the tree at all; if it can, the ray is left pending
-#pragma unroll 1
-      for (int r = 0; r < NR; r++) {
-        const bool on = go && (r == 0 || (flags & F_HAS_SHADOW));
-        if (!__any_sync(kFull, on)) continue;
-        if (on) {
-          const F3 d = r == 0 ? d0 : d1;
-          const F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-          float t = 3.0e38f;
-          int id = -1;
-          flat_hits<COUNT>(sc, o, d, inv, t, id, tc);
-          n_rays++;
-          const bool pd = TREE && sc.n_nodes > 0 && bvh_bounds_hit(sc, o, inv, t < 3.0e38f ? t * 1.0001f + 1e-4f : 3.0e38f);
-          if (r == 0) { t0 = t; id0 = id; pend0 = pd; } else { t1 = t; id1 = id; pend1 = pd; }
-        }
-      }
+      // the vertex itself: the code of persistent.cuh's phase A, on the variables loaded above
+#include "path_vertex.inc"
 
       if (go) {
         SLF(W_OX) = o.x; SLF(W_OY) = o.y; SLF(W_OZ) = o.z;

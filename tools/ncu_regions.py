@@ -65,6 +65,8 @@ for r in rows[2:]:
         key = "dp:" + fn(s_[1])
     elif s_[0] == "persistent.cuh":
         key = "pk:%d" % (s_[1] // 25 * 25)
+    elif s_[0] == "path_vertex.inc":
+        key = "pv:%d" % (s_[1] // 25 * 25)
     elif s_[0] in ("pool.cuh", "cpool.cuh"):
         g = int(os.environ.get("REGION_LINES", "10"))
         key = "%s:%d" % (s_[0], s_[1] // g * g)

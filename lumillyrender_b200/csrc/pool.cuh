@@ -23,6 +23,10 @@
 
 namespace lr {
 
+// Tunables, each settled by A/B runs on one box (profiles/r01_e_ab_s39.txt, s43-s49): paths per warp (64, 96 or 128: no gain
+// beyond 64), pending rays that start a BVH phase (24: slower, 48: same), resident CTAs per SM asked of the register
+// allocator (pt: 4..8 within 3 %, 6 = 80 registers; pt-direct: 4 = 127 registers without spills, its 42-word slots
+// allow 5 at most).
 #ifndef LR_POOL_SLOTS
 #define LR_POOL_SLOTS 64
 #endif
@@ -32,14 +36,8 @@ namespace lr {
 #ifndef LR_PMB_PT_TREE
 #define LR_PMB_PT_TREE 6
 #endif
-#ifndef LR_PMB_PT_FLAT
-#define LR_PMB_PT_FLAT 6
-#endif
 #ifndef LR_PMB_PTD_TREE
 #define LR_PMB_PTD_TREE 4
-#endif
-#ifndef LR_PMB_PTD_FLAT
-#define LR_PMB_PTD_FLAT 4
 #endif
 
 namespace pl {
@@ -96,7 +94,8 @@ LR_DEV int select_take(int* list, int lane, unsigned (&words)[N], int quota, int
 
 template <int INTEGRATOR, bool TREE>
 struct PoolMinBlocks {
-  static constexpr int value = INTEGRATOR == LR_INTEGRATOR_PT_DIRECT ? (TREE ? LR_PMB_PTD_TREE : LR_PMB_PTD_FLAT) : (TREE ? LR_PMB_PT_TREE : LR_PMB_PT_FLAT);
+  static_assert(TREE, "the pool kernel is built for scenes with a BVH only (persistent_inst.cu)");
+  static constexpr int value = INTEGRATOR == LR_INTEGRATOR_PT_DIRECT ? LR_PMB_PTD_TREE : LR_PMB_PT_TREE;
 };
 
 template <int INTEGRATOR, bool TREE, bool COUNT, int BUILD>

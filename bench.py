@@ -100,6 +100,16 @@ def oracle_sample(desc_owner, params_fn, spp, target_seconds=12.0):
     return st["samples"] / sec / 1e6, st["rays"] / sec / 1e6, st, desc, cores
 
 
+def reference_traversal(st):
+    """What the reference's own traversal costs per ray ('for context'): bvh.rs:131-141 visits every node
+    whose box the ray's LINE hits, unordered and unpruned, then fully tests every candidate leaf.  Counters of the
+    restatement; bytes at the reference's sizes (AABB 36 B per node visited, aabb.rs:10-14; 3 x 12 B of vertices per
+    primitive tested, triangle.rs:25-40)."""
+    rays = max(st.get("rays", 0), 1)
+    nodes, prims = st.get("nodes_visited", 0) / rays, st.get("prims_tested", 0) / rays
+    return {"nodes_per_ray": nodes, "prims_per_ray": prims, "bytes_per_ray": 36.0 * nodes + 36.0 * prims}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -128,6 +138,7 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
         "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": desc,
+                         "reference_traversal": reference_traversal(st),
                          "note": "C++ restatement of the reference CPU algorithm (oracle/); the Rust reference cannot be built offline"},
         "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -293,7 +304,7 @@ def main():
             from lumillyrender_b200.renderer import params_from_config
             ms, mr, ost, desc, cores = oracle_sample(d, lambda spp: params_from_config(d.config, spp=spp, seed=1), SPP_PER_GPU)
             line["cpu_baseline"] = {"value": ms, "unit": "Msamples/s", "mrays_per_s": mr, "cores": cores, "kind": "port", "sample": desc,
-                                    "oracle_bvh_build_s": ost["build_seconds"]}
+                                    "reference_traversal": reference_traversal(ost), "oracle_bvh_build_s": ost["build_seconds"]}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

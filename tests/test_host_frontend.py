@@ -341,3 +341,46 @@ def test_ibl_scene_uses_decoded_pixels(lr, assets):
     assert sky.type == 1 and sky.height == 256 and sky.n_pixels == 512 * 256
     px = np.ctypeslib.as_array(sky.pixels, shape=(256, 512, 3))
     assert px.max() > 5000 and px.min() >= 0
+
+
+def test_parallel_bvh_build_equals_sequential(lr, monkeypatch):
+    """bvh_build.cpp forks the top levels of the SAH build over the host's cores (LR_BVH_THREADS; 1 = sequential).  The
+    subtrees are concatenated in depth-first order with shifted child indices, so node array, triangle permutation,
+    flat list and depth are those of the sequential build, byte for byte — whatever the thread count."""
+    import ctypes as C
+    from lumillyrender_b200 import capi
+    rng = np.random.RandomState(5)
+    n = 70000                                                     # above twice the fork grain (16384)
+    centre = rng.uniform(-50, 50, (n, 1, 3))
+    tri = (centre + rng.normal(0, 0.4, (n, 3, 3))).astype(np.float32)
+    tri[:6] = rng.uniform(-60, 60, (6, 3, 3)).astype(np.float32)  # a few wall-sized triangles: the flat list
+    mats = (capi.LrMaterial * 1)()
+    mats[0].type = capi.LR_MAT_LAMBERT
+    T = (capi.LrTriangle * n)()
+    flat = np.ctypeslib.as_array(C.cast(T, C.POINTER(C.c_uint8)), shape=(n * C.sizeof(capi.LrTriangle),))
+    rec = np.zeros(n, dtype=np.dtype([("p", np.float32, 9), ("material", np.int32), ("prim_id", np.int32)]))
+    assert rec.dtype.itemsize == C.sizeof(capi.LrTriangle)
+    rec["p"] = tri.reshape(n, 9)
+    rec["prim_id"] = np.arange(n)
+    flat[:] = rec.view(np.uint8)
+    lib = capi.load_library()
+    m = (C.c_float * 16)()
+    lib.lr_matrix_look_at(F(0, 0, 200), F(0, 0, 0), F(0, 1, 0), m)
+    cam = capi.LrCamera()
+    lib.lr_camera_ideal_pinhole(m, 60.0, 32, 32, C.byref(cam))
+    S = (capi.LrSphere * 0)()
+
+    def build(threads):
+        monkeypatch.setenv("LR_BVH_THREADS", str(threads))
+        d = lr.Description.from_arrays(mats, T, S, cam)
+        c = d.desc.contents
+        nodes = np.ctypeslib.as_array(C.cast(c.nodes, C.POINTER(C.c_uint8)), shape=(c.n_nodes * C.sizeof(capi.LrBvhNode),)).copy()
+        tris = np.ctypeslib.as_array(C.cast(c.triangles, C.POINTER(C.c_uint8)), shape=(c.n_triangles * C.sizeof(capi.LrTriangle),)).copy()
+        return nodes, tris, c.n_nodes, c.n_flat_triangles, c.bvh_depth
+
+    ref = build(1)
+    assert ref[2] > 20000 and ref[3] >= 1 and 10 < ref[4] < 64
+    for threads in (2, 3, 8, 64):
+        got = build(threads)
+        assert got[2:] == ref[2:], threads
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), threads

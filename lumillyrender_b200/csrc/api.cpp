@@ -11,6 +11,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.h"
@@ -193,21 +194,34 @@ int lr_scene_create(const LrSceneDesc* d, LrScene** out) {
       float4* mats = (float4*)(h + o_mats); float* cdf = (float*)(h + o_cdf); float4* emitters = (float4*)(h + o_emitters);
       float4* sky = (float4*)(h + o_sky);
       if (d->n_nodes > 0) std::memcpy(nodes, d->nodes, (size_t)d->n_nodes * sizeof(LrBvhNode));
-      for (int i = 0; i < d->n_triangles; i++) {
-        const LrTriangle& t = d->triangles[i];
-        // p0 and the edges of Moller-Trumbore, e1 = p1 - p0, e2 = p2 - p0 (triangle.rs:71-72): single fp32 subtractions
-        const Vec3 e1 = vsub(vec3(t.p1), vec3(t.p0)), e2 = vsub(vec3(t.p2), vec3(t.p0));
-        tris[3 * (size_t)i + 0] = mk4(t.p0[0], t.p0[1], t.p0[2], as_float(t.prim_id));
-        tris[3 * (size_t)i + 1] = mk4(e1[0], e1[1], e1[2], as_float(t.material));
-        tris[3 * (size_t)i + 2] = mk4(e2[0], e2[1], e2[2], 0.0f);
-        // Triangle::aabb (triangle.rs:102-119): min / max of the vertices
-        tri_box[2 * (size_t)i + 0] = mk4(std::fmin(std::fmin(t.p0[0], t.p1[0]), t.p2[0]), std::fmin(std::fmin(t.p0[1], t.p1[1]), t.p2[1]),
-                                         std::fmin(std::fmin(t.p0[2], t.p1[2]), t.p2[2]), 0.0f);
-        tri_box[2 * (size_t)i + 1] = mk4(std::fmax(std::fmax(t.p0[0], t.p1[0]), t.p2[0]), std::fmax(std::fmax(t.p0[1], t.p1[1]), t.p2[1]),
-                                         std::fmax(std::fmax(t.p0[2], t.p1[2]), t.p2[2]), 0.0f);
-        // triangle.rs:36  normal = (p1 - p0).cross(p2 - p0).normalize(), in the reference's fp32 operation order
-        const Vec3 n = vnormalize(vcross(e1, e2));
-        tri_n[i] = mk4(n[0], n[1], n[2], 0.0f);
+      // the per-triangle work (edges, box, normal: ~40 flops each) is independent: large meshes are packed by a few threads,
+      // each writing its own range of the arena (lr_scene_create is inside the timed region of an end-to-end render)
+      auto pack_tris = [&](int i0, int i1) {
+        for (int i = i0; i < i1; i++) {
+          const LrTriangle& t = d->triangles[i];
+          // p0 and the edges of Moller-Trumbore, e1 = p1 - p0, e2 = p2 - p0 (triangle.rs:71-72): single fp32 subtractions
+          const Vec3 e1 = vsub(vec3(t.p1), vec3(t.p0)), e2 = vsub(vec3(t.p2), vec3(t.p0));
+          tris[3 * (size_t)i + 0] = mk4(t.p0[0], t.p0[1], t.p0[2], as_float(t.prim_id));
+          tris[3 * (size_t)i + 1] = mk4(e1[0], e1[1], e1[2], as_float(t.material));
+          tris[3 * (size_t)i + 2] = mk4(e2[0], e2[1], e2[2], 0.0f);
+          // Triangle::aabb (triangle.rs:102-119): min / max of the vertices
+          tri_box[2 * (size_t)i + 0] = mk4(std::fmin(std::fmin(t.p0[0], t.p1[0]), t.p2[0]), std::fmin(std::fmin(t.p0[1], t.p1[1]), t.p2[1]),
+                                           std::fmin(std::fmin(t.p0[2], t.p1[2]), t.p2[2]), 0.0f);
+          tri_box[2 * (size_t)i + 1] = mk4(std::fmax(std::fmax(t.p0[0], t.p1[0]), t.p2[0]), std::fmax(std::fmax(t.p0[1], t.p1[1]), t.p2[1]),
+                                           std::fmax(std::fmax(t.p0[2], t.p1[2]), t.p2[2]), 0.0f);
+          // triangle.rs:36  normal = (p1 - p0).cross(p2 - p0).normalize(), in the reference's fp32 operation order
+          const Vec3 n = vnormalize(vcross(e1, e2));
+          tri_n[i] = mk4(n[0], n[1], n[2], 0.0f);
+        }
+      };
+      {
+        const int hw = (int)std::thread::hardware_concurrency();
+        const int workers = d->n_triangles >= 65536 ? std::max(1, std::min(8, hw)) : 1;
+        std::vector<std::thread> pool;
+        const int per = (d->n_triangles + workers - 1) / workers;
+        for (int w = 1; w < workers; w++) pool.emplace_back(pack_tris, std::min(d->n_triangles, w * per), std::min(d->n_triangles, (w + 1) * per));
+        pack_tris(0, std::min(d->n_triangles, per));
+        for (std::thread& th : pool) th.join();
       }
       for (int i = 0; i < d->n_spheres; i++) {
         const LrSphere& sp = d->spheres[i];

@@ -74,3 +74,57 @@ def mc_agreement(mean_a, sumsq_a, n_a, mean_b, sumsq_b, n_b):
     z = abs(float(mean_a.mean()) - float(mean_b.mean())) / max(img_se, 1e-12)
     relmse = float(np.mean((mean_a - mean_b) ** 2 / (mean_b ** 2 + 1e-2)))
     return float(ok.mean()), z, relmse
+
+
+def form_factor_scene(lr_mod, albedo=0.6, emission=(10.0, 8.0, 6.0), half=(10.0, 15.0), height=50.0, point=(37.0, 41.0), with_mesh=False):
+    """A Lambert floor (y = 0) under a rectangular Lambert emitter of black albedo, parallel to it and centred above
+    `point` — which lies where the reference's hard-coded checker (lambert.rs:66-90) is 1 — seen by a 1-degree ideal
+    pinhole.  The reflected radiance at the point has a closed form: albedo * L_e * F with F the point-to-rectangle
+    form factor, for pt (emission found by BSDF sampling) and pt-direct (light sampling) alike.
+    with_mesh adds a cloud of 200 small black triangles beside the point (it neither shades nor lights it, but the scene
+    then has a BVH, so the kernels that traverse one are the ones tested).
+    Returns (Description, analytic RGB)."""
+    import math
+    from lumillyrender_b200 import capi
+    C = capi.C
+    a, b = half
+    px, pz = point
+    mats = (capi.LrMaterial * 3)()
+    mats[2].type = capi.LR_MAT_LAMBERT                      # black, no emission: the mesh cloud
+    mats[2].color[:] = [0.0, 0.0, 0.0]
+    mats[0].type = capi.LR_MAT_LAMBERT
+    mats[0].color[:] = [albedo] * 3
+    mats[1].type = capi.LR_MAT_LAMBERT
+    mats[1].color[:] = [0.0, 0.0, 0.0]                      # black: a path that reaches the light ends there
+    mats[1].emission[:] = list(emission)
+    n_mesh = 200 if with_mesh else 0
+    T = (capi.LrTriangle * (4 + n_mesh))()
+    big = 4000.0
+    quads = [([(-big, 0, -big), (-big, 0, big), (big, 0, big)], 0), ([(-big, 0, -big), (big, 0, big), (big, 0, -big)], 0),
+             # the light faces down: (p1 - p0) x (p2 - p0) = -y
+             ([(px - a, height, pz - b), (px + a, height, pz - b), (px + a, height, pz + b)], 1),
+             ([(px - a, height, pz - b), (px + a, height, pz + b), (px - a, height, pz + b)], 1)]
+    for i, (v, m) in enumerate(quads):
+        T[i].p0[:] = v[0]; T[i].p1[:] = v[1]; T[i].p2[:] = v[2]
+        T[i].material = m; T[i].prim_id = i
+    rng = np.random.RandomState(11)
+    for i in range(n_mesh):
+        c = np.array([px + 60.0, 15.0, pz]) + rng.uniform(-6, 6, 3)
+        v = (c + rng.normal(0, 0.8, (3, 3))).astype(np.float32)
+        T[4 + i].p0[:] = v[0]; T[4 + i].p1[:] = v[1]; T[4 + i].p2[:] = v[2]
+        T[4 + i].material = 2; T[4 + i].prim_id = 4 + i
+    lib = capi.load_library()
+    mtx = (C.c_float * 16)()
+    # The reference's look_at stores the basis as rows and M*v applies it untransposed (SURVEY.md Q9): a view tilted inside
+    # the yz-plane comes out with its tilt mirrored.  Aiming at the mirror image of the point (height +25 above the eye)
+    # therefore looks DOWN at it; the tests check with the primary-hit probe that the centre ray lands on the point.
+    lib.lr_matrix_look_at((C.c_float * 3)(px, 25.0, pz + 20.0), (C.c_float * 3)(px, 50.0, pz), (C.c_float * 3)(0, 1, 0), mtx)
+    cam = capi.LrCamera()
+    lib.lr_camera_ideal_pinhole(mtx, 1.0, 8, 8, C.byref(cam))
+    S = (capi.LrSphere * 0)()
+    d = lr_mod.Description.from_arrays(mats, T, S, cam)     # sky: black by default
+
+    def corner(x, y, h):                                     # form factor of a rectangle x * y with a corner above the point
+        return (x / math.hypot(x, h) * math.atan(y / math.hypot(x, h)) + y / math.hypot(y, h) * math.atan(x / math.hypot(y, h))) / (2 * math.pi)
+    f = 4.0 * corner(a, b, height)
+    return d, np.array([albedo * e * f for e in emission])

@@ -390,3 +390,25 @@ def test_math_modes_agree_statistically(lr, orc, assets):
     assert close > 0.7
     frac, z, relmse = mc_agreement(a / spp, asq, spp, b / spp, bsq, spp)
     assert frac >= 0.99 and z <= 4.0
+
+
+@pytest.mark.parametrize("integrator", [0, 1])
+def test_direct_lighting_matches_the_point_to_rectangle_form_factor(lr, orc, integrator):
+    """An independent pin for what the reference's own tests leave open (emission, Lambert BRDF and sampling, the light
+    sampling of scene.rs:104-151 with its geometry term and pdf): a closed-form answer.  Floor point under a rectangular
+    emitter: L = albedo * L_e * F(point -> rectangle), for pt and for pt-direct."""
+    from conftest import form_factor_scene
+    d, exact = form_factor_scene(lr)
+    o = orc.OracleScene(d.desc, keepalive=d)
+    prim, t = o.trace_primary()
+    assert set(np.unique(prim)) <= {0, 1} and np.allclose(t, math.hypot(25.0, 20.0), rtol=1e-2), "the camera must look at the floor point"
+    spp = 4096 if integrator == 1 else 16384
+    p = make_params(lr, d.config, integrator=integrator, spp=spp, seed=3, depth=5, depth_limit=64, no_direct_emitter=0)
+    s, sq, st = o.render(p, traversal=0)
+    n = spp * s.shape[0] * s.shape[1]
+    mean = s.sum(axis=(0, 1)) / n
+    var = sq.sum(axis=(0, 1)) / n - mean ** 2
+    se = np.sqrt(np.maximum(var, 0.0) / n)
+    assert st["nonfinite_samples"] == 0
+    assert np.all(np.abs(mean - exact) <= 4.0 * se + 1e-4 * exact), (mean, exact, se)
+    assert np.all(se < 0.01 * exact), "the test must be sharp: standard error below 1 % of the answer"

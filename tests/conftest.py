@@ -76,11 +76,14 @@ def mc_agreement(mean_a, sumsq_a, n_a, mean_b, sumsq_b, n_b):
     return float(ok.mean()), z, relmse
 
 
-def form_factor_scene(lr_mod, albedo=0.6, emission=(10.0, 8.0, 6.0), half=(10.0, 15.0), height=50.0, point=(37.0, 41.0), with_mesh=False):
+def form_factor_scene(lr_mod, albedo=0.6, emission=(10.0, 8.0, 6.0), half=(10.0, 15.0), height=50.0, point=(37.0, 41.0), with_mesh=False, sphere_light=0.0):
     """A Lambert floor (y = 0) under a rectangular Lambert emitter of black albedo, parallel to it and centred above
     `point` — which lies where the reference's hard-coded checker (lambert.rs:66-90) is 1 — seen by a 1-degree ideal
     pinhole.  The reflected radiance at the point has a closed form: albedo * L_e * F with F the point-to-rectangle
     form factor, for pt (emission found by BSDF sampling) and pt-direct (light sampling) alike.
+    sphere_light = r > 0 replaces the rectangle by a spherical emitter of radius r centred at the same height: the form
+    factor of a sphere seen from straight below is (r / height)^2 (Sphere::sample, sphere.rs:79-84, samples the whole
+    sphere; its far side fails the closest-hit distance match of scene.rs:127-132).
     with_mesh adds a cloud of 200 small black triangles beside the point (it neither shades nor lights it, but the scene
     then has a BVH, so the kernels that traverse one are the ones tested).
     Returns (Description, analytic RGB)."""
@@ -104,6 +107,10 @@ def form_factor_scene(lr_mod, albedo=0.6, emission=(10.0, 8.0, 6.0), half=(10.0,
              # the light faces down: (p1 - p0) x (p2 - p0) = -y
              ([(px - a, height, pz - b), (px + a, height, pz - b), (px + a, height, pz + b)], 1),
              ([(px - a, height, pz - b), (px + a, height, pz + b), (px - a, height, pz + b)], 1)]
+    if sphere_light > 0.0:
+        # the two light triangles shrink to a speck far away, without emission (the count and the indices stay the same)
+        quads[2] = ([(9000.0, 1.0, 9000.0), (9000.1, 1.0, 9000.0), (9000.0, 1.0, 9000.1)], 2)
+        quads[3] = ([(9001.0, 1.0, 9000.0), (9001.1, 1.0, 9000.0), (9001.0, 1.0, 9000.1)], 2)
     for i, (v, m) in enumerate(quads):
         T[i].p0[:] = v[0]; T[i].p1[:] = v[1]; T[i].p2[:] = v[2]
         T[i].material = m; T[i].prim_id = i
@@ -121,10 +128,12 @@ def form_factor_scene(lr_mod, albedo=0.6, emission=(10.0, 8.0, 6.0), half=(10.0,
     lib.lr_matrix_look_at((C.c_float * 3)(px, 25.0, pz + 20.0), (C.c_float * 3)(px, 50.0, pz), (C.c_float * 3)(0, 1, 0), mtx)
     cam = capi.LrCamera()
     lib.lr_camera_ideal_pinhole(mtx, 1.0, 8, 8, C.byref(cam))
-    S = (capi.LrSphere * 0)()
+    S = (capi.LrSphere * (1 if sphere_light > 0.0 else 0))()
+    if sphere_light > 0.0:
+        S[0].center[:] = [px, height, pz]; S[0].radius = sphere_light; S[0].material = 1; S[0].prim_id = 4 + n_mesh
     d = lr_mod.Description.from_arrays(mats, T, S, cam)     # sky: black by default
 
     def corner(x, y, h):                                     # form factor of a rectangle x * y with a corner above the point
         return (x / math.hypot(x, h) * math.atan(y / math.hypot(x, h)) + y / math.hypot(y, h) * math.atan(x / math.hypot(y, h))) / (2 * math.pi)
-    f = 4.0 * corner(a, b, height)
+    f = 4.0 * corner(a, b, height) if sphere_light <= 0.0 else (sphere_light / height) ** 2
     return d, np.array([albedo * e * f for e in emission])

@@ -284,18 +284,19 @@ def test_render_multi_single_process(scenes, lr, gpu, monkeypatch):
     assert np.array_equal(few, solo) and stf["rays"] == sts["rays"]
 
 
+@pytest.mark.parametrize("sphere_light", [0.0, 8.0])
 @pytest.mark.parametrize("integrator,with_mesh", [(0, False), (1, False), (0, True), (1, True)])
-def test_direct_lighting_matches_the_point_to_rectangle_form_factor(lr, gpu, integrator, with_mesh):
+def test_direct_lighting_matches_the_point_to_rectangle_form_factor(lr, gpu, integrator, with_mesh, sphere_light):
     """The closed-form check of tests/test_oracle_known_answers.py on the CUDA path: a floor point under a rectangular
     emitter reflects albedo * L_e * F(point -> rectangle), for pt (BSDF sampling finds the light) and pt-direct (light
     sampling).  with_mesh puts a BVH into the scene: pt then runs the pool kernel, pt-direct the deferred-traversal one."""
     from conftest import form_factor_scene
-    d, exact = form_factor_scene(lr, with_mesh=with_mesh)
+    d, exact = form_factor_scene(lr, with_mesh=with_mesh, sphere_light=sphere_light)   # 8.0: spherical emitter, F = (r / h)^2
     assert (d.desc.contents.n_nodes > 0) == with_mesh
     s = d.scene()
     prim, t = s.trace_primary()
     assert set(np.unique(prim)) <= {0, 1}, "the camera must look at the floor"
-    spp = 16384 if integrator == 1 else 65536
+    spp = (16384 if integrator == 1 else 65536) * (4 if sphere_light > 0 else 1)
     img, sq, st = s.render(integrator=integrator, spp=spp, seed=3, depth=5, depth_limit=64, no_direct_emitter=0, sumsq=True)
     n = spp * img.shape[0] * img.shape[1]
     mean = img.mean(axis=(0, 1), dtype=np.float64)

@@ -392,17 +392,18 @@ def test_math_modes_agree_statistically(lr, orc, assets):
     assert frac >= 0.99 and z <= 4.0
 
 
+@pytest.mark.parametrize("sphere_light", [0.0, 8.0])
 @pytest.mark.parametrize("integrator", [0, 1])
-def test_direct_lighting_matches_the_point_to_rectangle_form_factor(lr, orc, integrator):
+def test_direct_lighting_matches_the_point_to_rectangle_form_factor(lr, orc, integrator, sphere_light):
     """An independent pin for what the reference's own tests leave open (emission, Lambert BRDF and sampling, the light
     sampling of scene.rs:104-151 with its geometry term and pdf): a closed-form answer.  Floor point under a rectangular
     emitter: L = albedo * L_e * F(point -> rectangle), for pt and for pt-direct."""
     from conftest import form_factor_scene
-    d, exact = form_factor_scene(lr)
+    d, exact = form_factor_scene(lr, sphere_light=sphere_light)      # 8.0: a spherical emitter, F = (r / h)^2
     o = orc.OracleScene(d.desc, keepalive=d)
     prim, t = o.trace_primary()
     assert set(np.unique(prim)) <= {0, 1} and np.allclose(t, math.hypot(25.0, 20.0), rtol=1e-2), "the camera must look at the floor point"
-    spp = 4096 if integrator == 1 else 16384
+    spp = (4096 if integrator == 1 else 16384) * (4 if sphere_light > 0 else 1)
     p = make_params(lr, d.config, integrator=integrator, spp=spp, seed=3, depth=5, depth_limit=64, no_direct_emitter=0)
     s, sq, st = o.render(p, traversal=0)
     n = spp * s.shape[0] * s.shape[1]

@@ -137,3 +137,45 @@ def form_factor_scene(lr_mod, albedo=0.6, emission=(10.0, 8.0, 6.0), half=(10.0,
         return (x / math.hypot(x, h) * math.atan(y / math.hypot(x, h)) + y / math.hypot(y, h) * math.atan(x / math.hypot(y, h))) / (2 * math.pi)
     f = 4.0 * corner(a, b, height) if sphere_light <= 0.0 else (sphere_light / height) ** 2
     return d, np.array([albedo * e * f for e in emission])
+
+
+def lens_cos4_case(lr_mod, kind, w=12, h=8):
+    """An empty scene under a radiance-1 sky seen through a lens camera ("thin-lens" or "pinhole" = the reference's realistic
+    pinhole) and the image it must produce: per pixel the mean of cos^4 over the pixel area and the aperture disc, cos
+    between (aperture point - sensor point) and the optical axis.  Returns (Description, expected HxW image)."""
+    from lumillyrender_b200 import capi
+    C = capi.C
+    lib = capi.load_library()
+    F = lambda *v: (C.c_float * len(v))(*v)
+    cam = capi.LrCamera()
+    if kind == "thin-lens":
+        m = (C.c_float * 16)()
+        lib.lr_matrix_look_at(F(0, 0, 10), F(0, 0, 0), F(0, 1, 0), m)
+        assert lib.lr_camera_thin_lens(m, 70.0, 60.0, 1.4, w, h, C.byref(cam)) == 0
+    else:
+        assert lib.lr_camera_pinhole(F(0, 0, 60), F(0, 0, 10), F(70.0, 70.0 * h / w), w, h, 9.0, C.byref(cam)) == 0
+    sky = capi.LrSky()
+    sky.type = capi.LR_SKY_UNIFORM
+    sky.color[:] = [1.0, 1.0, 1.0]
+    mats = (capi.LrMaterial * 1)()
+    d = lr_mod.Description.from_arrays(mats, (capi.LrTriangle * 0)(), (capi.LrSphere * 0)(), cam, sky)
+    fwd, right, up = (np.array(list(v), dtype=np.float64) for v in (cam.forward, cam.right, cam.up))
+    pos, apc = np.array(list(cam.position), dtype=np.float64), np.array(list(cam.aperture_position), dtype=np.float64)
+    sx, sy, ra = cam.sensor_size[0], cam.sensor_size[1], cam.aperture_radius
+    assert ra > 1.0 and cam.aperture_sensor_distance > 0
+    k = 6                                                       # midpoint nodes per pixel axis; 24 x 48 over the disc (equal areas)
+    jit = (np.arange(k) + 0.5) / k
+    rad = np.sqrt((np.arange(24) + 0.5) / 24) * ra
+    ang = (np.arange(48) + 0.5) / 48 * 2 * np.pi
+    disc = (rad[:, None, None] * (np.cos(ang)[None, :, None] * right + np.sin(ang)[None, :, None] * up)).reshape(-1, 3)
+    expect = np.zeros((h, w))
+    for y in range(h):
+        for x in range(w):
+            px = ((x + jit) / w - 0.5) * sx                      # camera.rs:64-81
+            py = ((y + jit) / h - 0.5) * sy
+            sensor = pos - px[:, None, None] * right + py[None, :, None] * up
+            v = (apc + disc)[None, None] - sensor[:, :, None, :]
+            cos = (v @ fwd) / np.linalg.norm(v, axis=-1)
+            expect[y, x] = np.mean(cos ** 4)
+    assert expect.min() < 0.6 and expect.max() > 0.9, "the vignetting must be visible in this set-up"
+    return d, expect

@@ -307,6 +307,21 @@ def test_direct_lighting_matches_the_point_to_rectangle_form_factor(lr, gpu, int
     assert np.all(se < 0.005 * exact)
 
 
+@pytest.mark.parametrize("kind", ["thin-lens", "pinhole"])
+def test_lens_cameras_image_a_uniform_sky_as_cos4(lr, gpu, kind):
+    """The radiometric camera pin of tests/test_oracle_known_answers.py on the CUDA path: a radiance-1 sky through the
+    thin-lens / realistic-pinhole camera is the cos^4 vignetting averaged over pixel and aperture."""
+    from conftest import lens_cos4_case
+    d, expect = lens_cos4_case(lr, kind)
+    s = d.scene()
+    spp = 200000
+    img, sq, st = s.render(integrator=0, spp=spp, seed=5, depth=5, depth_limit=64, no_direct_emitter=0, sumsq=True)
+    mean = img[..., 0].astype(np.float64)
+    se = np.sqrt(np.maximum(sq[..., 0].astype(np.float64) / spp - mean ** 2, 0.0) / spp)
+    assert st["nonfinite_samples"] == 0
+    assert np.all(np.abs(mean - expect) <= 4.5 * se + 2e-3 * expect), float(np.abs(mean - expect).max())
+
+
 def test_error_paths(scenes, lr):
     from lumillyrender_b200.capi import LumillyError
     d, s, o = scenes("primitive")

@@ -413,3 +413,21 @@ def test_direct_lighting_matches_the_point_to_rectangle_form_factor(lr, orc, int
     assert st["nonfinite_samples"] == 0
     assert np.all(np.abs(mean - exact) <= 4.0 * se + 1e-4 * exact), (mean, exact, se)
     assert np.all(se < 0.01 * exact), "the test must be sharp: standard error below 1 % of the answer"
+
+
+@pytest.mark.parametrize("kind", ["thin-lens", "pinhole"])
+def test_lens_cameras_image_a_uniform_sky_as_cos4(lr, orc, kind):
+    """Radiometric pin for the realistic-pinhole and thin-lens cameras (camera.rs:224-328, 366-476), which no reference
+    test covers: with nothing but a radiance-1 sky the measurement equation L * g * sensitivity / pdf must come out as the
+    cos^4 vignetting, cos being the angle between (aperture point - sensor point) and the optical axis, averaged over the
+    pixel and the aperture disc (conftest.lens_cos4_case integrates it with a midpoint rule from the camera block's
+    geometry alone: no random numbers, no camera code)."""
+    from conftest import lens_cos4_case
+    d, expect = lens_cos4_case(lr, kind)
+    o = orc.OracleScene(d.desc, keepalive=d)
+    spp = 20000
+    s, sq, st = o.render(make_params(lr, d.config, integrator=0, spp=spp, seed=5, depth=5, depth_limit=64, no_direct_emitter=0), traversal=0)
+    img = s[..., 0] / spp
+    se = np.sqrt(np.maximum(sq[..., 0] / spp - img ** 2, 0.0) / spp)
+    assert np.all(np.abs(img - expect) <= 4.5 * se + 2e-3 * expect), float(np.abs(img - expect).max())
+    assert np.all(se < 0.004)

@@ -69,6 +69,13 @@ def test_compute_calls_fail_loudly_without_a_gpu(lr, assets):
     assert e.value.code in (-2, -3)
     with pytest.raises(LumillyError):
         lr.measure_l2_read_gbs()
+    # the single-process multi-GPU entry: argument errors first, then the same loud refusal
+    with pytest.raises(LumillyError) as e:
+        d.render_multi([0, 1, 2, 3, 4, 5, 6, 7, 8], spp=2)
+    assert e.value.code == -1
+    with pytest.raises(LumillyError) as e:
+        d.render_multi([0], spp=2)
+    assert e.value.code == -2 and "no CPU fallback" in e.value.message
 
 
 def test_scene_validation_rejects_bad_descriptions(lr):

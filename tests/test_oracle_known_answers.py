@@ -548,3 +548,52 @@ def test_lens_cameras_image_a_uniform_sky_as_cos4(lr, orc, kind):
     se = np.sqrt(np.maximum(sq[..., 0] / spp - img ** 2, 0.0) / spp)
     assert np.all(np.abs(img - expect) <= 4.5 * se + 2e-3 * expect), float(np.abs(img - expect).max())
     assert np.all(se < 0.004)
+
+
+@pytest.mark.parametrize("integrator", [0, 1])
+def test_emissive_cavity_closed_forms(lr, orc, integrator):
+    """Integrator structure against closed forms (scene.rs:20-46, 64-193; Q3, Q5): inside a closed cube whose Lambert
+    walls (albedo rho, where the hard-coded checker is 1) all emit L_e towards the inside, pure path tracing must
+    return L_e / (1 - rho) — emission at every vertex, forced continuation up to `depth`, Russian roulette with
+    p = max albedo beyond it, all unbiased — while pt-direct returns L_e alone: it counts emission at the first vertex
+    only and its light sampling contributes nothing at an emissive surface (scene.rs:104-110)."""
+    from lumillyrender_b200 import capi
+    lib = capi.load_library()
+    rho, le = 0.5, np.array([1.0, 0.5, 0.25])
+    c, hs = np.array([37.0, 0.0, 41.0]), 4.0                   # x in [33, 41], z in [37, 45]: checker == 1 (lambert.rs:66-90)
+    mats = (capi.LrMaterial * 1)()
+    mats[0].type = capi.LR_MAT_LAMBERT
+    mats[0].color[:] = [rho] * 3
+    mats[0].emission[:] = list(le)
+    quads = []
+    for axis in range(3):
+        for sign in (-1.0, 1.0):
+            u, v = [a for a in range(3) if a != axis]
+            corners = []
+            for du, dv in ((-1, -1), (1, -1), (1, 1), (-1, 1)):
+                p = c.copy(); p[axis] += sign * hs; p[u] += du * hs; p[v] += dv * hs
+                corners.append(p)
+            for tri in ((0, 1, 2), (0, 2, 3)):
+                p0, p1, p2 = (corners[i] for i in tri)
+                if np.dot(np.cross(p1 - p0, p2 - p0), c - p0) < 0:   # emission is one-sided: the geometric normal must face inside
+                    p1, p2 = p2, p1
+                quads.append((p0, p1, p2))
+    T = (capi.LrTriangle * 12)()
+    for i, (p0, p1, p2) in enumerate(quads):
+        T[i].p0[:] = list(p0); T[i].p1[:] = list(p1); T[i].p2[:] = list(p2)
+        T[i].material = 0; T[i].prim_id = i
+    m = (C.c_float * 16)()
+    lib.lr_matrix_look_at(F(*c), F(c[0], c[1], c[2] - 1.0), F(0, 1, 0), m)      # from the centre along -z
+    cam = capi.LrCamera()
+    lib.lr_camera_ideal_pinhole(m, 60.0, 8, 8, C.byref(cam))
+    d = lr.Description.from_arrays(mats, T, (capi.LrSphere * 0)(), cam)
+    o = orc.OracleScene(d.desc, keepalive=d)
+    spp = 8192
+    s, sq, st = o.render(make_params(lr, d.config, integrator=integrator, spp=spp, seed=4, depth=5, depth_limit=64, no_direct_emitter=0), traversal=0)
+    n = spp * 64
+    mean = s.sum(axis=(0, 1)) / n
+    se = np.sqrt(np.maximum(sq.sum(axis=(0, 1)) / n - mean ** 2, 0.0) / n)
+    exact = le / (1.0 - rho) if integrator == 0 else le
+    assert st["nonfinite_samples"] == 0
+    assert np.all(np.abs(mean - exact) <= 4.0 * se + 1e-4 * exact), (mean, exact, se)
+    assert np.all(se < 0.005 * exact)

@@ -597,3 +597,48 @@ def test_emissive_cavity_closed_forms(lr, orc, integrator):
     assert st["nonfinite_samples"] == 0
     assert np.all(np.abs(mean - exact) <= 4.0 * se + 1e-4 * exact), (mean, exact, se)
     assert np.all(se < 0.005 * exact)
+
+
+@pytest.mark.parametrize("offset", [0.0, 1.3, -0.7])
+def test_ibl_lookup_matches_an_independent_restatement(orc, offset):
+    """IBLSky::radiance (sky.rs:57-79) has no reference test: nearest texel of a 2H x H equirect image, theta from
+    acos(d.y), phi from atan2(d.z, d.x), wrapped with `%`.  A sky whose texel value IS its index is looked up for the
+    axes (known by hand for offset 0) and for random directions against the formula written separately in numpy."""
+    from lumillyrender_b200 import capi
+    L = orc.lib()
+    H = 16
+    W = 2 * H
+    pix = np.zeros((H * W, 3), dtype=np.float32)
+    pix[:, 0] = np.arange(H * W)                                 # r = texel index, g = row, b = column
+    pix[:, 1] = np.arange(H * W) // W
+    pix[:, 2] = np.arange(H * W) % W
+    sky = capi.LrSky()
+    sky.type = capi.LR_SKY_IBL
+    sky.pixels = pix.ctypes.data_as(C.POINTER(C.c_float))
+    sky.n_pixels = H * W
+    sky.height = H
+    sky.longitude_offset = offset
+
+    def look(d):
+        out = F(0, 0, 0)
+        L.orc_sky_radiance(C.byref(sky), F(*d), out)
+        return int(out[1]), int(out[2])                          # (row, column)
+
+    if offset == 0.0:
+        assert look((0, 1, 0))[0] == 0                           # straight up: theta = 0 -> first row
+        assert look((0, -1, 0)) == (0, W // 2)                   # straight down: theta / pi == 1 wraps to row 0 (`% 1.0`); phi = atan2(0, 0) = 0
+        assert look((1, 0, 0)) == (H // 2, W // 2)               # phi = 0 -> u = 0.5
+        assert look((0, 0, 1)) == (H // 2, 3 * W // 4)           # phi = pi/2 -> u = 0.75
+        assert look((0, 0, -1)) == (H // 2, W // 4)              # phi = -pi/2 -> u = 0.25
+    rng = np.random.RandomState(2)
+    agree = 0
+    n = 2000
+    for _ in range(n):
+        d = np.array(normalize(rng.normal(size=3).tolist()), dtype=np.float32)
+        theta = math.acos(float(d[1]))
+        phi = math.atan2(float(d[2]), float(d[0]))
+        u = math.fmod((phi + math.pi + offset) / (2.0 * math.pi), 1.0)
+        v = math.fmod(theta / math.pi, 1.0)
+        x, y = max(0, math.floor(W * u)), max(0, math.floor(H * v))     # `as usize` saturates negatives to 0
+        agree += look(d.tolist()) == ((y * W + x) % (H * W) // W, (y * W + x) % (H * W) % W)
+    assert agree >= n - 4, agree                                 # fp32 vs fp64 at a texel boundary may differ on a few

@@ -642,3 +642,50 @@ def test_ibl_lookup_matches_an_independent_restatement(orc, offset):
         x, y = max(0, math.floor(W * u)), max(0, math.floor(H * v))     # `as usize` saturates negatives to 0
         agree += look(d.tolist()) == ((y * W + x) % (H * W) // W, (y * W + x) % (H * W) % W)
     assert agree >= n - 4, agree                                 # fp32 vs fp64 at a texel boundary may differ on a few
+
+
+def test_camera_samples_match_hand_geometry(orc):
+    """Camera::sample of the ideal pinhole, the omnidirectional and the thin-lens camera (camera.rs:100-115, 168-188,
+    458-476) for explicit random numbers, against geometry worked out by hand: no reference test covers them."""
+    from lumillyrender_b200 import capi
+    L = orc.lib()
+    m = (C.c_float * 16)()
+    L.orc_matrix_look_at(F(0, 0, 10), F(0, 0, 0), F(0, 1, 0), m)
+    w, h = 4, 2
+    out = (C.c_float * 9)()
+    # ---- omnidirectional: direction = (sin t cos p, sin t sin p, cos t), p = (x + u) / W * 2 pi, t = (y + v) / H * pi;
+    # the matrix only supplies the origin (the orientation is NOT applied, as in the reference)
+    cam = capi.LrCamera()
+    L.orc_camera_omnidirectional(m, w, h, C.byref(cam))
+    for x, y, u, v in ((0, 0, 0.0, 0.5), (1, 0, 0.0, 1.0 - 1e-7), (2, 1, 0.5, 0.0), (3, 1, 0.25, 0.75)):
+        L.orc_camera_sample(C.byref(cam), x, y, u, v, 0.5, 0.5, out)
+        p, t = (x + u) / w * 2 * math.pi, (y + v) / h * math.pi
+        assert np.allclose(list(out)[0:3], [0, 0, 10])
+        assert np.allclose(list(out)[3:6], [math.sin(t) * math.cos(p), math.sin(t) * math.sin(p), math.cos(t)], atol=2e-6)
+        assert list(out)[6:9] == [1.0, 1.0, 1.0]                # pdf, geometry term, sensitivity
+    # ---- ideal pinhole looking down -z from (0, 0, 10), fov 90 degrees: the sensor is 100 wide, 50 behind the aperture;
+    # pixel (x, y) with (u, v) = (0.5, 0.5) looks through the aperture towards the mirrored sensor point
+    L.orc_camera_ideal_pinhole(m, 90.0, w, h, C.byref(cam))
+    sx, sy = 2 * 50.0 * math.tan(math.radians(45.0)), 2 * 50.0 * math.tan(math.radians(45.0)) * h / w
+    assert abs(cam.sensor_size[0] - sx) < 1e-3 and abs(cam.sensor_size[1] - sy) < 1e-3
+    for x, y in ((0, 0), (3, 1), (1, 0)):
+        L.orc_camera_sample(C.byref(cam), x, y, 0.5, 0.5, 0.5, 0.5, out)
+        px, py = ((x + 0.5) / w - 0.5) * sx, ((y + 0.5) / h - 0.5) * sy
+        # sensor point = position - right * px + up * py, 50 behind the aperture: the ray leaves with (+px, -py, -50) normalised
+        exp = np.array([px, -py, -50.0]) / math.sqrt(px * px + py * py + 2500.0)
+        assert np.allclose(list(out)[0:3], [0, 0, 10]) and np.allclose(list(out)[3:6], exp, atol=2e-6), (list(out), exp)
+        assert list(out)[6:9] == [1.0, 1.0, 1.0]
+    # ---- thin lens: every ray through the aperture that starts at one sensor point meets the same point of the focus plane
+    focus = 40.0
+    L.orc_camera_thin_lens(m, 60.0, focus, 2.0, w, h, C.byref(cam))
+    f = 1.0 / (1.0 / 50.0 + 1.0 / focus)
+    assert abs(cam.aperture_radius - f / 2.0 / 2.0) < 1e-4      # f / f_number / 2 (camera.rs:387-389)
+    hits = []
+    for ua, va in ((0.0, 0.0), (0.25, 1.0 - 1e-7), (0.6, 0.5), (0.9, 0.9)):
+        L.orc_camera_sample(C.byref(cam), 3, 0, 0.3, 0.8, ua, va, out)
+        o, d = np.array(list(out)[0:3]), np.array(list(out)[3:6])
+        assert abs(np.linalg.norm(d) - 1.0) < 1e-5
+        tt = (10.0 - focus - o[2]) / d[2]                        # the plane `focus` in front of the aperture (z = 10 - focus)
+        hits.append(o + tt * d)
+        assert abs(np.linalg.norm(o - np.array([0, 0, 10.0])) - math.sqrt(va) * cam.aperture_radius) < 1e-4
+    assert np.allclose(hits, hits[0], atol=2e-3), hits

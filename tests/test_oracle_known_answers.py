@@ -689,3 +689,34 @@ def test_camera_samples_match_hand_geometry(orc):
         hits.append(o + tt * d)
         assert abs(np.linalg.norm(o - np.array([0, 0, 10.0])) - math.sqrt(va) * cam.aperture_radius) < 1e-4
     assert np.allclose(hits, hits[0], atol=2e-3), hits
+
+
+@pytest.mark.parametrize("ior", [1.5, 2.4, 1.0001])
+def test_glass_sphere_in_a_white_furnace_is_invisible(lr, orc, ior):
+    """Ideal refraction (ideal_refraction.rs:40-104) under a radiance-1 sky: reflection carries brdf * cos / pdf = 1,
+    refraction (to_ior / from_ior)^2 on the way in and its inverse on the way out, so EVERY path returns exactly 1 —
+    a noise-free pin of the Fresnel roulette, of the 1 / (in . n) factors and of the unoriented-normal cosine (scene.rs:91)
+    working together, total internal reflection included."""
+    from lumillyrender_b200 import capi
+    lib = capi.load_library()
+    mats = (capi.LrMaterial * 1)()
+    mats[0].type = capi.LR_MAT_IDEAL_REFRACTION
+    mats[0].color[:] = [1.0, 1.0, 1.0]
+    mats[0].param0, mats[0].param1 = 0.0, ior                   # no absorption
+    S = (capi.LrSphere * 1)()
+    S[0].center[:] = [0, 0, 0]; S[0].radius = 1.0; S[0].material = 0; S[0].prim_id = 0
+    m = (C.c_float * 16)()
+    lib.lr_matrix_look_at(F(0, 0, 5), F(0, 0, 0), F(0, 1, 0), m)
+    cam = capi.LrCamera()
+    lib.lr_camera_ideal_pinhole(m, 30.0, 16, 16, C.byref(cam))
+    sky = capi.LrSky()
+    sky.type = capi.LR_SKY_UNIFORM
+    sky.color[:] = [1.0, 1.0, 1.0]
+    d = lr.Description.from_arrays(mats, (capi.LrTriangle * 0)(), S, cam, sky)
+    o = orc.OracleScene(d.desc, keepalive=d)
+    prim, _ = o.trace_primary()
+    assert 0.3 < (prim >= 0).mean() < 0.7                       # the sphere fills about half of the view
+    spp = 64
+    s, _, st = o.render(make_params(lr, d.config, integrator=0, spp=spp, seed=4, depth=5, depth_limit=64, no_direct_emitter=0), traversal=0)
+    assert st["nonfinite_samples"] == 0 and st["rays"] > 1.5 * st["samples"]
+    assert np.allclose(s / spp, 1.0, atol=3e-6), (float((s / spp).min()), float((s / spp).max()))

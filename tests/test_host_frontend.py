@@ -384,3 +384,53 @@ def test_parallel_bvh_build_equals_sequential(lr, monkeypatch):
         got = build(threads)
         assert got[2:] == ref[2:], threads
         assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), threads
+
+
+@pytest.mark.parametrize("case", ["identical", "collinear-centroids", "one-giant-many-tiny"])
+def test_bvh_build_survives_degenerate_meshes(lr, monkeypatch, case):
+    """Meshes that defeat the SAH split (all centroids equal, all on one line, one triangle spanning the cloud): the build
+    must fall back to median splits, stay inside the traversal stack (depth < 64), reference every triangle exactly once,
+    and the forked build must still equal the sequential one."""
+    import ctypes as C
+    from lumillyrender_b200 import capi
+    rng = np.random.RandomState(9)
+    n = 40000
+    if case == "identical":
+        tri = np.tile(np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]]], dtype=np.float32), (n, 1, 1))
+    elif case == "collinear-centroids":
+        t = np.linspace(-100, 100, n, dtype=np.float32)[:, None, None]
+        tri = (np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]]], dtype=np.float32) * 0.01 + t * np.array([1, 0, 0], dtype=np.float32)).astype(np.float32)
+    else:
+        tri = (rng.uniform(-10, 10, (n, 1, 3)) + rng.normal(0, 0.01, (n, 3, 3))).astype(np.float32)
+        tri[0] = [[-10, -10, -10], [10, -10, 10], [0, 10, 0]]
+    mats = (capi.LrMaterial * 1)()
+    T = (capi.LrTriangle * n)()
+    rec = np.zeros(n, dtype=np.dtype([("p", np.float32, 9), ("material", np.int32), ("prim_id", np.int32)]))
+    rec["p"] = tri.reshape(n, 9)
+    rec["prim_id"] = np.arange(n)
+    np.ctypeslib.as_array(C.cast(T, C.POINTER(C.c_uint8)), shape=(n * C.sizeof(capi.LrTriangle),))[:] = rec.view(np.uint8)
+    lib = capi.load_library()
+    m = (C.c_float * 16)()
+    lib.lr_matrix_look_at(F(0, 0, 200), F(0, 0, 0), F(0, 1, 0), m)
+    cam = capi.LrCamera()
+    lib.lr_camera_ideal_pinhole(m, 60.0, 16, 16, C.byref(cam))
+
+    def build(threads):
+        monkeypatch.setenv("LR_BVH_THREADS", str(threads))
+        d = lr.Description.from_arrays(mats, T, (capi.LrSphere * 0)(), cam)
+        c = d.desc.contents
+        nodes = np.ctypeslib.as_array(C.cast(c.nodes, C.POINTER(C.c_int32)), shape=(c.n_nodes, 16)).copy()
+        prim = np.array([c.triangles[i].prim_id for i in range(0, c.n_triangles, 97)])
+        return nodes, c.n_triangles, c.n_flat_triangles, c.bvh_depth, prim
+
+    nodes, n_tri, n_flat, depth, prim = build(1)
+    assert n_tri == n and 0 < depth < 64
+    # every tree triangle is referenced by exactly one leaf: leaf code ~((first << 3) | (count - 1))
+    seen = np.zeros(n - n_flat, dtype=np.int32)
+    for code in nodes[:, 12:14].ravel():
+        if code < 0:
+            first, count = (~code) >> 3, ((~code) & 7) + 1
+            seen[first:first + count] += 1
+    assert np.all(seen == 1)
+    par = build(8)
+    assert np.array_equal(par[0], nodes) and par[1:4] == (n_tri, n_flat, depth) and np.array_equal(par[4], prim)

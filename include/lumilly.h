@@ -209,7 +209,9 @@ int lr_stats_fetch(const LrScene* scene, void* cuda_stream, LrStats* stats);
    (peer access; staged copies where peer access is unavailable), adds them in list order and divides by
    spp_count.  out_rgb / out_sumsq / stats as lr_render (stats are totals, kernel_ms the slowest device's).
    1 <= n_devices <= 8, device ids distinct.  The result for a given device COUNT is bit-reproducible and
-   differs from other counts only by fp32 summation order. */
+   differs from other counts only by fp32 summation order.  Not re-entrant: it switches the calling thread's
+   CUDA device (restored on return) and the library's current device, so call it from one thread at a time
+   and not concurrently with other entry points. */
 /* The sample-range sharding rule, for any host that shards by itself (one process per GPU): part `part` of
    `n_parts` of the range [spp_begin, spp_begin + spp_count) — consecutive ranges that tile it exactly, sizes
    differing by <= 1, the larger ones first.  lr_render_multi and bench.py's ranks use this rule. */

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -219,8 +220,15 @@ int lr_scene_create(const LrSceneDesc* d, LrScene** out) {
         const int workers = d->n_triangles >= 65536 ? std::max(1, std::min(8, hw)) : 1;
         std::vector<std::thread> pool;
         const int per = (d->n_triangles + workers - 1) / workers;
-        for (int w = 1; w < workers; w++) pool.emplace_back(pack_tris, std::min(d->n_triangles, w * per), std::min(d->n_triangles, (w + 1) * per));
+        int started = 1;                                         // ranges [0, started * per) are taken care of
+        try {
+          for (int w = 1; w < workers; w++) {
+            pool.emplace_back(pack_tris, std::min(d->n_triangles, w * per), std::min(d->n_triangles, (w + 1) * per));
+            started = w + 1;
+          }
+        } catch (const std::system_error&) {}                    // no thread to be had: this thread packs the rest
         pack_tris(0, std::min(d->n_triangles, per));
+        if (started < workers) pack_tris(std::min(d->n_triangles, started * per), d->n_triangles);
         for (std::thread& th : pool) th.join();
       }
       for (int i = 0; i < d->n_spheres; i++) {

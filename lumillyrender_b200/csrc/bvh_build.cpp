@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -181,9 +182,11 @@ struct Builder {
     }
     auto run = [&](int slot) { sub[slot] = build_forked(range[slot][0], range[slot][1], cbx[slot], depth + 1, forks - 1, sub_depth[slot]); };
     if (!leaf[0] && !leaf[1]) {
-      std::thread other(run, 0);
+      std::thread other;
+      bool forked = true;
+      try { other = std::thread(run, 0); } catch (const std::system_error&) { forked = false; }   // no thread to be had: build both here
       run(1);
-      other.join();
+      if (forked) other.join(); else run(0);
     } else {
       for (int slot = 0; slot < 2; slot++) if (!leaf[slot]) run(slot);
     }

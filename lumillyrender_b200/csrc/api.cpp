@@ -123,7 +123,7 @@ int lr_device_info(int* sm_count, int* l2_bytes, int* sm_clock_khz, char* name, 
   return LR_OK;
 }
 
-int lr_scene_create(const LrSceneDesc* d, LrScene** out) {
+static int lr_scene_create_body(const LrSceneDesc* d, LrScene** out) {
   if (!d || !out) return fail(LR_ERR_INVALID, "null argument");
   *out = nullptr;
   if (int rc = validate_desc(*d)) return rc;
@@ -297,6 +297,7 @@ int lr_scene_create(const LrSceneDesc* d, LrScene** out) {
   *out = s;
   return LR_OK;
 }
+int lr_scene_create(const LrSceneDesc* d, LrScene** out) { LR_GUARDED(lr_scene_create_body(d, out)); }
 
 void lr_scene_destroy(LrScene* s) {
   if (!s) return;
@@ -509,7 +510,7 @@ static int scene_clone(const LrScene* src, int src_device, int dst_device, LrSce
   return LR_OK;
 }
 
-int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_devices, const int32_t* devices, float* out_rgb,
+static int lr_render_multi_body(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_devices, const int32_t* devices, float* out_rgb,
                     float* out_sumsq, LrStats* stats) {
   if (!desc || !p || !devices || !out_rgb) return fail(LR_ERR_INVALID, "null argument");
   if (n_devices < 1 || n_devices > kMaxPeers) return fail(LR_ERR_INVALID, "lr_render_multi takes 1..8 devices");
@@ -667,6 +668,10 @@ int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_
   if (rc != LR_OK) { g_error = err; return rc; }
   if (stats) *stats = total;
   return LR_OK;
+}
+int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_devices, const int32_t* devices, float* out_rgb,
+                    float* out_sumsq, LrStats* stats) {
+  LR_GUARDED(lr_render_multi_body(desc, p, n_devices, devices, out_rgb, out_sumsq, stats));
 }
 
 int lr_trace_primary(const LrScene* s, float u, float v, float ua, float va, int32_t* prim, float* t) {

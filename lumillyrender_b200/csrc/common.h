@@ -44,3 +44,13 @@ inline float sphere_area(float r) { return 4.0f * kHostPI * (r * r); }
 int validate_desc(const LrSceneDesc& d);          // scene_validate.cpp
 
 }  // namespace lr
+
+// Nothing may throw across the C ABI: entry points that allocate on the host run their body through this.
+#define LR_GUARDED(call)                                                                                   \
+  try {                                                                                                    \
+    return (call);                                                                                         \
+  } catch (const std::bad_alloc&) {                                                                        \
+    return lr::fail(LR_ERR_UNSUPPORTED, "out of host memory");                                             \
+  } catch (const std::exception& e__) {                                                                    \
+    return lr::fail(LR_ERR_INVALID, std::string("internal error: ") + e__.what());                         \
+  }

@@ -406,7 +406,7 @@ int lr_host_scene_load(const char* toml_path, const char* asset_root, int32_t ow
   return LR_OK;
 }
 
-int lr_host_scene_from_arrays(const LrMaterial* materials, int32_t n_materials, const LrTriangle* triangles, int32_t n_triangles,
+static int lr_host_scene_from_arrays_body(const LrMaterial* materials, int32_t n_materials, const LrTriangle* triangles, int32_t n_triangles,
                               const LrSphere* spheres, int32_t n_spheres, const LrCamera* camera, const LrSky* sky, LrHostScene** out) {
   if (!out || !camera || n_materials < 0 || n_triangles < 0 || n_spheres < 0) return fail(LR_ERR_INVALID, "bad argument");
   if ((n_materials && !materials) || (n_triangles && !triangles) || (n_spheres && !spheres)) return fail(LR_ERR_INVALID, "null array with non-zero count");
@@ -430,6 +430,10 @@ int lr_host_scene_from_arrays(const LrMaterial* materials, int32_t n_materials, 
   if (int rc = hs->finalize()) return rc;
   *out = hs.release();
   return LR_OK;
+}
+int lr_host_scene_from_arrays(const LrMaterial* materials, int32_t n_materials, const LrTriangle* triangles, int32_t n_triangles,
+                              const LrSphere* spheres, int32_t n_spheres, const LrCamera* camera, const LrSky* sky, LrHostScene** out) {
+  LR_GUARDED(lr_host_scene_from_arrays_body(materials, n_materials, triangles, n_triangles, spheres, n_spheres, camera, sky, out));
 }
 
 const LrSceneDesc* lr_host_scene_desc(const LrHostScene* hs) { return hs ? &hs->desc : nullptr; }

@@ -140,7 +140,7 @@ using namespace lr;
 
 extern "C" {
 
-int lr_save_png(const char* path, const float* rgb, int32_t w, int32_t h, float gamma) {
+static int lr_save_png_body(const char* path, const float* rgb, int32_t w, int32_t h, float gamma) {
   if (!path || !rgb || w <= 0 || h <= 0) return fail(LR_ERR_INVALID, "bad argument");
   std::vector<unsigned char> raw((size_t)h * (1 + (size_t)w * 3));
   for (int y = 0; y < h; y++) {
@@ -166,8 +166,9 @@ int lr_save_png(const char* path, const float* rgb, int32_t w, int32_t h, float 
   std::fclose(f);
   return ok ? LR_OK : fail(LR_ERR_IO, std::string("short write to `") + path + "`");
 }
+int lr_save_png(const char* path, const float* rgb, int32_t w, int32_t h, float gamma) { LR_GUARDED(lr_save_png_body(path, rgb, w, h, gamma)); }
 
-int lr_save_hdr(const char* path, const float* rgb, int32_t w, int32_t h) {
+static int lr_save_hdr_body(const char* path, const float* rgb, int32_t w, int32_t h) {
   if (!path || !rgb || w <= 0 || h <= 0) return fail(LR_ERR_INVALID, "bad argument");
   FILE* f = std::fopen(path, "wb");
   if (!f) return fail(LR_ERR_IO, std::string("cannot create `") + path + "`");
@@ -185,8 +186,9 @@ int lr_save_hdr(const char* path, const float* rgb, int32_t w, int32_t h) {
   std::fclose(f);
   return ok ? LR_OK : fail(LR_ERR_IO, std::string("short write to `") + path + "`");
 }
+int lr_save_hdr(const char* path, const float* rgb, int32_t w, int32_t h) { LR_GUARDED(lr_save_hdr_body(path, rgb, w, h)); }
 
-int lr_load_hdr(const char* path, float** rgb, int32_t* w, int32_t* h) {
+static int lr_load_hdr_body(const char* path, float** rgb, int32_t* w, int32_t* h) {
   if (!path || !rgb || !w || !h) return fail(LR_ERR_INVALID, "bad argument");
   std::vector<float> px;
   int ww = 0, hh = 0;
@@ -197,6 +199,7 @@ int lr_load_hdr(const char* path, float** rgb, int32_t* w, int32_t* h) {
   *rgb = out; *w = ww; *h = hh;
   return LR_OK;
 }
+int lr_load_hdr(const char* path, float** rgb, int32_t* w, int32_t* h) { LR_GUARDED(lr_load_hdr_body(path, rgb, w, h)); }
 
 void lr_free(void* p) { std::free(p); }
 

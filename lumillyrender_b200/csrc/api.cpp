@@ -79,6 +79,7 @@ struct LrScene {
   mutable cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   mutable bool ev_pending = false;
   bool has_ggx = false;                            // selects the render kernel built with GGX inline
+  int device = 0, sm_count = 1;                    // the device that owns every pointer above, and its SM count
 };
 
 extern "C" {
@@ -174,7 +175,9 @@ static int lr_scene_create_body(const LrSceneDesc* d, LrScene** out) {
   const size_t upload_bytes = total;
   const size_t o_counters = take(C_COUNT * sizeof(unsigned long long));
 
-  LrScene* s = new LrScene();
+  struct SceneGuard { LrScene* s; ~SceneGuard() { if (s) lr_scene_destroy(s); } } guard{new LrScene()};   // released on success
+  LrScene* s = guard.s;
+  s->device = g_device; s->sm_count = std::max(g_sm_count, 1);
   cudaError_t e = cudaSuccess;
   DevScene& dv = s->dev;
   float area = 0.0f;
@@ -218,18 +221,20 @@ static int lr_scene_create_body(const LrSceneDesc* d, LrScene** out) {
       {
         const int hw = (int)std::thread::hardware_concurrency();
         const int workers = d->n_triangles >= 65536 ? std::max(1, std::min(8, hw)) : 1;
-        std::vector<std::thread> pool;
+        // joined on every way out of this scope: a joinable std::thread that is destroyed calls std::terminate
+        struct Joiner { std::vector<std::thread> v; ~Joiner() { for (std::thread& th : v) if (th.joinable()) th.join(); } } pool;
+        pool.v.reserve(workers);                                 // no reallocation (and no bad_alloc) while threads run
         const int per = (d->n_triangles + workers - 1) / workers;
         int started = 1;                                         // ranges [0, started * per) are taken care of
         try {
           for (int w = 1; w < workers; w++) {
-            pool.emplace_back(pack_tris, std::min(d->n_triangles, w * per), std::min(d->n_triangles, (w + 1) * per));
+            pool.v.emplace_back(pack_tris, std::min(d->n_triangles, w * per), std::min(d->n_triangles, (w + 1) * per));
             started = w + 1;
           }
         } catch (const std::system_error&) {}                    // no thread to be had: this thread packs the rest
         pack_tris(0, std::min(d->n_triangles, per));
         if (started < workers) pack_tris(std::min(d->n_triangles, started * per), d->n_triangles);
-        for (std::thread& th : pool) th.join();
+        for (std::thread& th : pool.v) th.join();
       }
       for (int i = 0; i < d->n_spheres; i++) {
         const LrSphere& sp = d->spheres[i];
@@ -275,11 +280,7 @@ static int lr_scene_create_body(const LrSceneDesc* d, LrScene** out) {
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev0, cudaEventDefault);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev1, cudaEventDefault);
-  if (e != cudaSuccess) {
-    const std::string msg = std::string("scene upload: ") + cudaGetErrorString(e);
-    lr_scene_destroy(s);
-    return fail(LR_ERR_CUDA, msg);
-  }
+  if (e != cudaSuccess) return fail(LR_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e));   // the guard frees the scene
   dv.n_nodes = d->n_nodes; dv.n_tris = d->n_triangles; dv.n_spheres = d->n_spheres; dv.n_emitters = (int)ems.size();
   dv.n_bvh_tris = d->n_triangles - d->n_flat_triangles;
   for (int k = 0; k < 3; k++) {
@@ -294,6 +295,7 @@ static int lr_scene_create_body(const LrSceneDesc* d, LrScene** out) {
   dv.cam = d->camera;
   s->width = d->camera.width; s->height = d->camera.height;
   for (int i = 0; i < d->n_materials; i++) s->has_ggx = s->has_ggx || d->materials[i].type == LR_MAT_GGX;
+  guard.s = nullptr;
   *out = s;
   return LR_OK;
 }
@@ -301,6 +303,11 @@ int lr_scene_create(const LrSceneDesc* d, LrScene** out) { LR_GUARDED(lr_scene_c
 
 void lr_scene_destroy(LrScene* s) {
   if (!s) return;
+  // work of this handle may still be in flight on a caller stream the legacy stream does not order against
+  if (s->ev_pending && s->ev1) cudaEventSynchronize(s->ev1);
+  int cur = -1;
+  const bool hop = cudaGetDevice(&cur) == cudaSuccess && cur != s->device && !s->allocs.empty();
+  if (hop) cudaSetDevice(s->device);                    // frees go to the owning device's stream
   for (void* p : s->allocs) dev_free(p);                // one block: scene arrays + the counter words
   dev_free(s->d_film);
   dev_free(s->d_film_sq);
@@ -308,6 +315,7 @@ void lr_scene_destroy(LrScene* s) {
   dev_free(s->d_partial_sq);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
+  if (hop) cudaSetDevice(cur);
   delete s;
 }
 
@@ -377,6 +385,13 @@ int lr_render_accumulate_device(const LrScene* s, const LrRenderParams* p, float
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const size_t n = (size_t)dp.crop_w * dp.crop_h * 3;
   float* ksum = d_sum; float* ksq = d_sumsq;
+  // The previous launch (possibly on a non-blocking stream the legacy stream does not order against) may still be using
+  // the partial buffers: wait for it BEFORE ensure_scratch can hand them back to the pool, and fold its time while here.
+  if (s->ev_pending) {
+    float ms = 0.0f;
+    if (cudaEventSynchronize(s->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) s->acc_kernel_ms += ms;
+    s->ev_pending = false;
+  }
   if (dp.splits > 1) {
     if (int rc = ensure_scratch(&s->d_partial, &s->partial_floats, n * dp.splits)) return rc;
     ksum = s->d_partial;
@@ -385,18 +400,13 @@ int lr_render_accumulate_device(const LrScene* s, const LrRenderParams* p, float
       ksq = s->d_partial_sq;
     }
   }
-  if (s->ev_pending) {   // fold the previous launch's time before reusing the events
-    float ms = 0.0f;
-    if (cudaEventSynchronize(s->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) s->acc_kernel_ms += ms;
-    s->ev_pending = false;
-  }
   LR_CUDA(cudaEventRecord(s->ev0, st));
   {
     // the unit cursor lives in the last word of the counter block (reset on the stream before every launch)
     unsigned int* next_unit = reinterpret_cast<unsigned int*>(s->d_counters + C_NEXT_UNIT);
     LR_CUDA(cudaMemsetAsync(next_unit, 0, sizeof(unsigned long long), st));
     LR_CUDA(launch_render_persistent(s->dev, dp, s->has_ggx, p->count_traversal != 0, ksum, d_sumsq ? ksq : nullptr, s->d_counters, next_unit,
-                                     std::max(g_sm_count, 1), st));
+                                     std::max(s->sm_count, 1), st));
     s->acc_launches++;
   }
   if (dp.splits > 1) {
@@ -478,6 +488,7 @@ static int scene_clone(const LrScene* src, int src_device, int dst_device, LrSce
   *out = nullptr;
   if (src->allocs.size() != 1 || src->block_bytes == 0) return fail(LR_ERR_INVALID, "scene_clone: unexpected scene layout");
   LrScene* s = new LrScene();
+  s->device = dst_device; s->sm_count = std::max(g_sm_count, 1);       // lr_init(dst_device) ran just before
   char* block = nullptr;
   const char* from = (const char*)src->allocs[0];
   cudaError_t e = dev_alloc((void**)&block, src->block_bytes);

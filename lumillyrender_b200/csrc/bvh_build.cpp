@@ -44,6 +44,7 @@ struct Box {
 constexpr int kBins = 16;
 static int kLeafTarget = 2;        // stop splitting at <= 2 triangles (measured best of 1..8, profiles/r01_c_ab_s17.txt;
                                    // LR_LEAF_TARGET: development knob)
+constexpr int kDeviceStackDepth = 64;   // device_scene.h: kStackDepth
 constexpr int kLeafMax = 8;        // leaf code holds count-1 in 3 bits
 constexpr int kSahDepthLimit = 32; // deeper than this: median splits only, so depth <= 32 + log2(n) < 64
 constexpr int kFlatAllBelow = 16;  // scenes with this many triangles or fewer: no tree at all
@@ -213,7 +214,7 @@ struct Builder {
 
 }  // namespace
 
-int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, int& depth_out, float& seconds_out, int& n_flat_out) {
+int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, int& depth_out, float& seconds_out, int& n_flat_out, float origin_extent) {
   const auto t0 = std::chrono::steady_clock::now();
   if (const char* e = std::getenv("LR_LEAF_TARGET")) kLeafTarget = std::max(1, std::min(8, std::atoi(e)));
   nodes_out.clear();
@@ -277,6 +278,10 @@ int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, 
   Builder bld{tri_box, centroid, order, {}, 0, 0.0f};
   float extent = 0.0f;
   for (int k = 0; k < 3; k++) extent = std::fmax(extent, std::fmax(std::fabs(scene.lo[k]), std::fabs(scene.hi[k])));   // whole scene: ray origins lie on any surface
+  // ... and at the camera and on the spheres (origin_extent, from the caller: max |coordinate| of the aperture / sensor
+  // positions and of the spheres' boxes, a sphere's radius clamped to 16 x the triangles' extent — the far side of a
+  // ground sphere of radius 1e5 is not a place rays reach the mesh from)
+  extent = std::fmax(extent, std::fmin(origin_extent, 1e30f));
   bld.pad = 4e-6f * extent + 1e-30f;     // > the rounding error of (box - origin) * inv, see device_path.cuh
   bld.nodes.reserve((size_t)n / 2 + 16);
   if (n == 1) {
@@ -315,7 +320,7 @@ int validate_desc(const LrSceneDesc& d) {
   if (d.n_flat_triangles < 0 || d.n_flat_triangles > d.n_triangles) return fail(LR_ERR_INVALID, "n_flat_triangles out of range");
   const int n_bvh_tris = d.n_triangles - d.n_flat_triangles;
   if ((n_bvh_tris > 0) != (d.n_nodes > 0)) return fail(LR_ERR_INVALID, "BVH nodes must be present iff triangles are in the BVH (use lr_host_scene_from_arrays)");
-  if (d.bvh_depth >= 64) return fail(LR_ERR_UNSUPPORTED, "BVH deeper than the device traversal stack (64)");
+
   const int n_prims = d.n_triangles + d.n_spheres;
   for (int i = 0; i < d.n_materials; i++)
     if (d.materials[i].type < LR_MAT_LAMBERT || d.materials[i].type > LR_MAT_IDEAL_REFRACTION) return fail(LR_ERR_INVALID, "unknown material type");
@@ -338,6 +343,31 @@ int validate_desc(const LrSceneDesc& d) {
         if (first < 0 || first + count > n_bvh_tris) return fail(LR_ERR_INVALID, "BVH leaf range out of bounds");
       }
     }
+  }
+  // The device traversal has a fixed stack and no cycle check (device_path.cuh), and the node array comes over a public
+  // ABI: walk the tree from node 0 and demand that it IS a tree — every inner node reached exactly once — whose real
+  // depth fits the stack.  The caller's bvh_depth is not trusted.
+  if (d.n_nodes > 0) {
+    std::vector<int> depth_of(d.n_nodes, 0);                 // 0 = not reached yet
+    std::vector<int> todo;
+    todo.push_back(0);
+    depth_of[0] = 1;
+    int reached = 0, max_depth = 0;
+    while (!todo.empty()) {
+      const int i = todo.back();
+      todo.pop_back();
+      reached++;
+      max_depth = std::max(max_depth, depth_of[i]);
+      for (int k = 0; k < 2; k++) {
+        const int c = d.nodes[i].c[k];
+        if (c < 0) continue;
+        if (depth_of[c] != 0) return fail(LR_ERR_INVALID, "BVH node reached twice (cycle or shared subtree)");
+        depth_of[c] = depth_of[i] + 1;
+        todo.push_back(c);
+      }
+    }
+    if (reached != d.n_nodes) return fail(LR_ERR_INVALID, "BVH has nodes that cannot be reached from the root");
+    if (max_depth >= kDeviceStackDepth) return fail(LR_ERR_UNSUPPORTED, "BVH deeper than the device traversal stack (64)");
   }
   const LrCamera& c = d.camera;
   if (c.type < LR_CAM_IDEAL_PINHOLE || c.type > LR_CAM_OMNIDIRECTIONAL) return fail(LR_ERR_INVALID, "unknown camera type");

@@ -367,7 +367,15 @@ int LrHostScene::finalize() {
   float seconds = 0.0f;
   int depth = 0;
   int n_flat = 0;
-  if (int rc = build_bvh(triangles, nodes, depth, seconds, n_flat)) return rc;
+  // where rays start besides the triangles: the camera and the spheres (the pad of the node boxes scales with it, bvh_build.cpp)
+  float tri_extent = 0.0f, origin_extent = 0.0f;
+  for (const LrTriangle& t : triangles)
+    for (int k = 0; k < 3; k++) tri_extent = std::fmax(tri_extent, std::fmax(std::fabs(t.p0[k]), std::fmax(std::fabs(t.p1[k]), std::fabs(t.p2[k]))));
+  for (int k = 0; k < 3; k++)
+    origin_extent = std::fmax(origin_extent, std::fmax(std::fabs(desc.camera.position[k]), std::fabs(desc.camera.aperture_position[k])));
+  for (const LrSphere& sp : spheres)
+    for (int k = 0; k < 3; k++) origin_extent = std::fmax(origin_extent, std::fabs(sp.center[k]) + std::fmin(std::fabs(sp.radius), 16.0f * tri_extent));
+  if (int rc = build_bvh(triangles, nodes, depth, seconds, n_flat, origin_extent)) return rc;
   desc.n_flat_triangles = n_flat;
   desc.materials = materials.data(); desc.n_materials = (int)materials.size();
   desc.triangles = triangles.data(); desc.n_triangles = (int)triangles.size();

@@ -55,7 +55,7 @@ void camera_omnidirectional(const Mat4& m, int w, int h, LrCamera& out);
 void camera_pinhole(Vec3 position, Vec3 aperture_position, const float* sensor_size, int w, int h, float aperture_radius, LrCamera& out);
 
 // permutes `tris`: BVH leaf order first, then the `n_flat_out` large triangles kept outside the BVH
-int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, int& depth_out, float& seconds_out, int& n_flat_out);
+int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, int& depth_out, float& seconds_out, int& n_flat_out, float origin_extent = 0.0f);
 
 int load_hdr_file(const std::string& path, std::vector<float>& rgb, int& w, int& h);
 

@@ -287,9 +287,12 @@ void load_mtl(const std::string& path, std::vector<ObjMaterial>& mats) {
       while (!m.name.empty() && (m.name.back() == ' ' || m.name.back() == '\t')) m.name.pop_back();
       mats.push_back(m);
     } else if (std::strncmp(p, "Kd", 2) == 0 && (p[2] == ' ' || p[2] == '\t') && !mats.empty()) {
+      // a malformed Kd (fewer than 3 numbers) leaves the components it does not define at tobj's default of 0
       char* e = nullptr;
       const char* q = p + 2;
-      for (int i = 0; i < 3; i++) { mats.back().diffuse[i] = std::strtof(q, &e); q = e; }
+      float kd[3] = {0.0f, 0.0f, 0.0f};
+      for (int i = 0; i < 3; i++) { kd[i] = std::strtof(q, &e); if (e == q) { kd[i] = 0.0f; break; } q = e; }
+      for (int i = 0; i < 3; i++) mats.back().diffuse[i] = kd[i];
     }
   }
 }
@@ -319,9 +322,16 @@ int load_obj(const std::string& path, ObjFile& out) {
     if (!eol) eol = end;
     const char* q = skip_sp(p);
     if (q[0] == 'v' && (q[1] == ' ' || q[1] == '\t')) {
+      // strtof skips '\n': a short line ("v 1 2") must not borrow the first number of the next line
       char* e = nullptr;
       q += 1;
-      for (int i = 0; i < 3; i++) { pos.push_back(std::strtof(q, &e)); if (e == q) return fail(LR_ERR_PARSE, path + ":" + std::to_string(lineno) + ": malformed vertex"); q = e; }
+      for (int i = 0; i < 3; i++) {
+        q = skip_sp(q);
+        const float x = q < eol ? std::strtof(q, &e) : 0.0f;
+        if (q >= eol || e == q || e > eol) return fail(LR_ERR_PARSE, path + ":" + std::to_string(lineno) + ": malformed vertex");
+        pos.push_back(x);
+        q = e;
+      }
     } else if (q[0] == 'f' && (q[1] == ' ' || q[1] == '\t')) {
       corner.clear();
       q += 1;
@@ -349,8 +359,11 @@ int load_obj(const std::string& path, ObjFile& out) {
       while (!name.empty() && (name.back() == '\r' || name.back() == ' ')) name.pop_back();
       cur.name = name.empty() ? "unnamed_object" : name;
     } else if (std::strncmp(q, "usemtl", 6) == 0 && (q[6] == ' ' || q[6] == '\t')) {
-      std::string name(skip_sp(q + 6), eol);
-      while (!name.empty() && (name.back() == '\r' || name.back() == ' ')) name.pop_back();
+      // tobj 0.1.6 looks up the first whitespace-delimited word after the keyword (`words.next()`)
+      const char* w0 = skip_sp(q + 6);
+      const char* w1 = w0;
+      while (w1 < eol && *w1 != ' ' && *w1 != '\t' && *w1 != '\r') w1++;
+      std::string name(w0, w1);
       int id = -1;
       for (size_t i = 0; i < out.materials.size(); i++) if (out.materials[i].name == name) id = (int)i;
       if (!cur.positions.empty() && id != cur.material_id) flush();

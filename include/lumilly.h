@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LR_ABI_VERSION 2
+#define LR_ABI_VERSION 3
 
 typedef enum LrStatus {
   LR_OK = 0,
@@ -219,6 +219,32 @@ int lr_shard_range(int32_t spp_begin, int32_t spp_count, int32_t part, int32_t n
 
 int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* params, int32_t n_devices, const int32_t* devices,
                     float* out_rgb, float* out_sumsq, LrStats* stats);
+
+/* ---- AOVs: Scene::normal / Scene::depth (src/scene.rs:48-62) of the camera ray of every sample in
+ * [spp_begin, spp_begin + spp_count) — the very camera rays lr_render draws for those samples (same seed, same
+ * stream) — averaged per pixel in sample order.  Honours seed / spp range / crop of `params`; integrator, depth,
+ * splits are ignored.  out: crop_w*crop_h*3 floats for LR_AOV_NORMAL (hit ? n/2 + 0.5 : 0), crop_w*crop_h floats
+ * for LR_AOV_DEPTH (hit ? Intersection.distance : 0).  Host pointer, synchronous.                              */
+typedef enum LrAovKind { LR_AOV_NORMAL = 0, LR_AOV_DEPTH = 1 } LrAovKind;
+int lr_render_aov(const LrScene* scene, const LrRenderParams* params, int32_t kind, float* out);
+
+/* ---- progressive / resumable rendering: the progress hook the reference abandoned (src/main.rs:81-91) as a handle.
+ * An LrFilm owns the per-pixel SUM buffers of one render (and the sums of squares if asked for) on the scene's device
+ * and remembers how many sample indices it holds.  lr_film_render adds the next `spp_count` sample indices (it
+ * overrides params->spp_begin with the film's count; seed / integrator / depths / crop must stay what the film was
+ * created with); lr_film_read gives the mean so far; lr_film_save / lr_film_load write and restore a checkpoint
+ * (raw sums + the parameters), in this or another process.  With params->splits == 1 every pixel's samples are added
+ * in sample order starting from the stored sum — the fold of main.rs:92-104 — so ANY cut of [0, n) into
+ * consecutive lr_film_render calls, with or without a save / load in between, gives bit for bit the image of one
+ * lr_render over [0, n).  (splits != 1 is deterministic but adds per-call partial sums.)                          */
+typedef struct LrFilm LrFilm;
+int lr_film_create(const LrScene* scene, const LrRenderParams* params, int32_t want_sumsq, LrFilm** out);
+int lr_film_render(LrFilm* film, int32_t spp_count, LrStats* stats /* nullable */);
+int lr_film_info(const LrFilm* film, int32_t* spp_done, int32_t* crop_w, int32_t* crop_h, int32_t* has_sumsq);   /* each nullable */
+int lr_film_read(const LrFilm* film, float* out_rgb /* mean so far */, float* out_sumsq /* nullable */);
+int lr_film_save(const LrFilm* film, const char* path);
+int lr_film_load(const LrScene* scene, const char* path, LrFilm** out);
+void lr_film_destroy(LrFilm* film);
 
 /* ---- parity probe: nearest hit of the primary ray through every film pixel with the
  * sensor jitter fixed to (u,v) and the aperture sample fixed to (ua,va).

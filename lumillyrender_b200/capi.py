@@ -15,6 +15,7 @@ LR_MAT_LAMBERT, LR_MAT_PHONG, LR_MAT_BLINN_PHONG, LR_MAT_GGX, LR_MAT_IDEAL_REFRA
 LR_CAM_IDEAL_PINHOLE, LR_CAM_PINHOLE, LR_CAM_THIN_LENS, LR_CAM_OMNIDIRECTIONAL = range(4)
 LR_SKY_UNIFORM, LR_SKY_IBL = 0, 1
 LR_INTEGRATOR_PT, LR_INTEGRATOR_PT_DIRECT = 0, 1
+LR_AOV_NORMAL, LR_AOV_DEPTH = 0, 1
 
 f32, i32, u64, i64 = C.c_float, C.c_int32, C.c_uint64, C.c_int64
 
@@ -98,6 +99,14 @@ SIGNATURES = {
     "lr_stats_fetch": (C.c_int, [_VP, _VP, C.POINTER(LrStats)]),
     "lr_shard_range": (C.c_int, [i32, i32, i32, i32, _PI, _PI]),
     "lr_render_multi": (C.c_int, [C.POINTER(LrSceneDesc), C.POINTER(LrRenderParams), i32, _PI, _PF, _PF, C.POINTER(LrStats)]),
+    "lr_render_aov": (C.c_int, [_VP, C.POINTER(LrRenderParams), i32, _PF]),
+    "lr_film_create": (C.c_int, [_VP, C.POINTER(LrRenderParams), i32, C.POINTER(_VP)]),
+    "lr_film_render": (C.c_int, [_VP, i32, C.POINTER(LrStats)]),
+    "lr_film_info": (C.c_int, [_VP, _PI, _PI, _PI, _PI]),
+    "lr_film_read": (C.c_int, [_VP, _PF, _PF]),
+    "lr_film_save": (C.c_int, [_VP, C.c_char_p]),
+    "lr_film_load": (C.c_int, [_VP, C.c_char_p, C.POINTER(_VP)]),
+    "lr_film_destroy": (None, [_VP]),
     "lr_trace_primary": (C.c_int, [_VP, f32, f32, f32, f32, _PI, _PF]),
     "lr_trace_rays": (C.c_int, [_VP, i64, _PF, _PF, _PI, _PF, _PF]),
     "lr_measure_l2_read_gbs": (C.c_int, [u64, C.c_int, _PF]),

@@ -473,6 +473,24 @@ int lr_render(const LrScene* s, const LrRenderParams* p, float* out_rgb, float* 
   return rc;
 }
 
+int lr_render_aov(const LrScene* s, const LrRenderParams* p, int32_t kind, float* out) {
+  if (!s || !p || !out) return fail(LR_ERR_INVALID, "null argument");
+  if (kind != LR_AOV_NORMAL && kind != LR_AOV_DEPTH) return fail(LR_ERR_INVALID, "unknown AOV kind");
+  LrRenderParams q = *p;
+  q.integrator = LR_INTEGRATOR_PT;                      // not used by the AOVs
+  DevParams dp;
+  if (int rc = resolve_params(s, &q, dp)) return rc;
+  if (int rc = ensure_device()) return rc;
+  const size_t n = (size_t)dp.crop_w * dp.crop_h * (kind == LR_AOV_NORMAL ? 3 : 1);
+  float* d_out = nullptr;
+  LR_CUDA(dev_alloc((void**)&d_out, n * sizeof(float)));
+  cudaError_t e = launch_aov(s->dev, dp, kind, d_out, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost);
+  dev_free(d_out);
+  if (e != cudaSuccess) return fail(LR_ERR_CUDA, std::string("render_aov: ") + cudaGetErrorString(e));
+  return LR_OK;
+}
+
 int lr_shard_range(int32_t spp_begin, int32_t spp_count, int32_t part, int32_t n_parts, int32_t* begin, int32_t* count) {
   if (!begin || !count) return fail(LR_ERR_INVALID, "null argument");
   if (n_parts <= 0 || part < 0 || part >= n_parts || spp_count < 0 || spp_begin < 0) return fail(LR_ERR_INVALID, "bad shard request");
@@ -721,6 +739,167 @@ int lr_trace_rays(const LrScene* s, int64_t n, const float* origins, const float
   if (e != cudaSuccess) return fail(LR_ERR_CUDA, std::string("trace_rays: ") + cudaGetErrorString(e));
   return LR_OK;
 }
+
+// ---------------------------------------------------------------- progressive / resumable rendering (main.rs:81-91)
+}  // extern "C"
+
+struct LrFilm {
+  const LrScene* scene = nullptr;
+  LrRenderParams params{};               // spp_begin = first sample index of the film, spp_count unused
+  int32_t spp_done = 0;
+  int32_t crop_w = 0, crop_h = 0;        // resolved window
+  float* d_sum = nullptr;
+  float* d_sumsq = nullptr;
+};
+
+namespace {
+constexpr char kFilmMagic[8] = {'L', 'R', 'F', 'I', 'L', 'M', '1', 0};
+struct FilmHeader {                      // checkpoint file: this header, then crop_w*crop_h*3 floats (and again for the squares)
+  char magic[8];
+  int32_t film_w, film_h, crop_x, crop_y, crop_w, crop_h;
+  int32_t integrator, depth, depth_limit, no_direct_emitter, splits, spp_begin, spp_done, has_sumsq;
+  uint64_t seed;
+};
+
+int film_alloc(const LrScene* s, const LrRenderParams* p, int want_sumsq, LrFilm** out) {
+  if (!s || !p || !out) return fail(LR_ERR_INVALID, "null argument");
+  *out = nullptr;
+  LrRenderParams probe = *p;
+  probe.spp_count = 1;
+  DevParams dp;
+  if (int rc = resolve_params(s, &probe, dp)) return rc;
+  if (int rc = ensure_device()) return rc;
+  LrFilm* f = new LrFilm();
+  f->scene = s; f->params = *p; f->params.spp_count = 0;
+  f->crop_w = dp.crop_w; f->crop_h = dp.crop_h;
+  const size_t bytes = (size_t)dp.crop_w * dp.crop_h * 3 * sizeof(float);
+  cudaError_t e = dev_alloc((void**)&f->d_sum, bytes);
+  if (e == cudaSuccess) e = cudaMemset(f->d_sum, 0, bytes);
+  if (e == cudaSuccess && want_sumsq) e = dev_alloc((void**)&f->d_sumsq, bytes);
+  if (e == cudaSuccess && want_sumsq) e = cudaMemset(f->d_sumsq, 0, bytes);
+  if (e != cudaSuccess) {
+    const std::string msg = std::string("film: ") + cudaGetErrorString(e);
+    lr_film_destroy(f);
+    return fail(LR_ERR_CUDA, msg);
+  }
+  *out = f;
+  return LR_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int lr_film_create(const LrScene* s, const LrRenderParams* p, int32_t want_sumsq, LrFilm** out) { LR_GUARDED(film_alloc(s, p, want_sumsq, out)); }
+
+void lr_film_destroy(LrFilm* f) {
+  if (!f) return;
+  cudaDeviceSynchronize();
+  dev_free(f->d_sum);
+  dev_free(f->d_sumsq);
+  delete f;
+}
+
+int lr_film_info(const LrFilm* f, int32_t* spp_done, int32_t* crop_w, int32_t* crop_h, int32_t* has_sumsq) {
+  if (!f) return fail(LR_ERR_INVALID, "null argument");
+  if (spp_done) *spp_done = f->spp_done;
+  if (crop_w) *crop_w = f->crop_w;
+  if (crop_h) *crop_h = f->crop_h;
+  if (has_sumsq) *has_sumsq = f->d_sumsq ? 1 : 0;
+  return LR_OK;
+}
+
+int lr_film_render(LrFilm* f, int32_t spp_count, LrStats* stats) {
+  if (!f) return fail(LR_ERR_INVALID, "null argument");
+  if (spp_count <= 0) return fail(LR_ERR_INVALID, "spp_count must be positive");
+  LrRenderParams q = f->params;
+  q.spp_begin = f->params.spp_begin + f->spp_done;
+  q.spp_count = spp_count;
+  LrStats dummy;
+  if (!stats) stats = &dummy;
+  if (int rc = lr_stats_fetch(f->scene, nullptr, stats)) return rc;       // drop counters of earlier calls
+  if (int rc = lr_render_accumulate_device(f->scene, &q, f->d_sum, f->d_sumsq, nullptr)) return rc;
+  if (int rc = lr_stats_fetch(f->scene, nullptr, stats)) return rc;       // synchronises: the samples are in the film
+  f->spp_done += spp_count;
+  return LR_OK;
+}
+
+int lr_film_read(const LrFilm* f, float* out_rgb, float* out_sumsq) {
+  if (!f || !out_rgb) return fail(LR_ERR_INVALID, "null argument");
+  if (out_sumsq && !f->d_sumsq) return fail(LR_ERR_INVALID, "the film was created without sums of squares");
+  if (f->spp_done <= 0) return fail(LR_ERR_INVALID, "the film holds no samples yet");
+  const size_t n = (size_t)f->crop_w * f->crop_h * 3;
+  float* d_tmp = nullptr;
+  LR_CUDA(dev_alloc((void**)&d_tmp, n * sizeof(float)));
+  cudaError_t e = cudaMemcpyAsync(d_tmp, f->d_sum, n * sizeof(float), cudaMemcpyDeviceToDevice, 0);
+  if (e == cudaSuccess) e = launch_scale(d_tmp, n, (float)f->spp_done, 0);            // main.rs:104
+  if (e == cudaSuccess) e = cudaMemcpy(out_rgb, d_tmp, n * sizeof(float), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && out_sumsq) e = cudaMemcpy(out_sumsq, f->d_sumsq, n * sizeof(float), cudaMemcpyDeviceToHost);
+  dev_free(d_tmp);
+  if (e != cudaSuccess) return fail(LR_ERR_CUDA, std::string("film read: ") + cudaGetErrorString(e));
+  return LR_OK;
+}
+
+static int film_save_body(const LrFilm* f, const char* path) {
+  if (!f || !path) return fail(LR_ERR_INVALID, "null argument");
+  const size_t n = (size_t)f->crop_w * f->crop_h * 3;
+  std::vector<float> host(n * (f->d_sumsq ? 2 : 1));
+  LR_CUDA(cudaMemcpy(host.data(), f->d_sum, n * sizeof(float), cudaMemcpyDeviceToHost));
+  if (f->d_sumsq) LR_CUDA(cudaMemcpy(host.data() + n, f->d_sumsq, n * sizeof(float), cudaMemcpyDeviceToHost));
+  FilmHeader h;
+  std::memset(&h, 0, sizeof(h));
+  std::memcpy(h.magic, kFilmMagic, 8);
+  const LrRenderParams& p = f->params;
+  h.film_w = f->scene->width; h.film_h = f->scene->height;
+  h.crop_x = p.crop_w > 0 ? p.crop_x : 0; h.crop_y = p.crop_w > 0 ? p.crop_y : 0; h.crop_w = f->crop_w; h.crop_h = f->crop_h;
+  h.integrator = p.integrator; h.depth = p.depth; h.depth_limit = p.depth_limit; h.no_direct_emitter = p.no_direct_emitter;
+  h.splits = p.splits; h.spp_begin = p.spp_begin; h.spp_done = f->spp_done; h.has_sumsq = f->d_sumsq ? 1 : 0; h.seed = p.seed;
+  // written next to the target and renamed: a crash mid-write never leaves a torn checkpoint under `path`
+  const std::string tmp = std::string(path) + ".part";
+  FILE* fp = std::fopen(tmp.c_str(), "wb");
+  if (!fp) return fail(LR_ERR_IO, std::string("cannot write `") + tmp + "`");
+  const bool ok = std::fwrite(&h, sizeof(h), 1, fp) == 1 && std::fwrite(host.data(), sizeof(float), host.size(), fp) == host.size();
+  const bool closed = std::fclose(fp) == 0;
+  if (!ok || !closed || std::rename(tmp.c_str(), path) != 0) { std::remove(tmp.c_str()); return fail(LR_ERR_IO, std::string("cannot write `") + path + "`"); }
+  return LR_OK;
+}
+int lr_film_save(const LrFilm* f, const char* path) { LR_GUARDED(film_save_body(f, path)); }
+
+static int film_load_body(const LrScene* s, const char* path, LrFilm** out) {
+  if (!s || !path || !out) return fail(LR_ERR_INVALID, "null argument");
+  *out = nullptr;
+  FILE* fp = std::fopen(path, "rb");
+  if (!fp) return fail(LR_ERR_IO, std::string("File `") + path + "` is not found.");
+  FilmHeader h;
+  std::vector<float> host;
+  int rc = LR_OK;
+  do {
+    if (std::fread(&h, sizeof(h), 1, fp) != 1 || std::memcmp(h.magic, kFilmMagic, 8) != 0) { rc = fail(LR_ERR_PARSE, "not a film checkpoint"); break; }
+    if (h.film_w != s->width || h.film_h != s->height) { rc = fail(LR_ERR_INVALID, "the checkpoint was made for another film resolution"); break; }
+    if (h.crop_w <= 0 || h.crop_h <= 0 || h.crop_x < 0 || h.crop_y < 0 || h.crop_x + h.crop_w > s->width || h.crop_y + h.crop_h > s->height ||
+        h.spp_done < 0 || h.spp_begin < 0) { rc = fail(LR_ERR_PARSE, "corrupt film checkpoint header"); break; }
+    const size_t n = (size_t)h.crop_w * h.crop_h * 3;
+    host.resize(n * (h.has_sumsq ? 2 : 1));
+    if (std::fread(host.data(), sizeof(float), host.size(), fp) != host.size()) { rc = fail(LR_ERR_PARSE, "truncated film checkpoint"); break; }
+  } while (0);
+  std::fclose(fp);
+  if (rc != LR_OK) return rc;
+  LrRenderParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.integrator = h.integrator; p.depth = h.depth; p.depth_limit = h.depth_limit; p.no_direct_emitter = h.no_direct_emitter;
+  p.splits = h.splits; p.spp_begin = h.spp_begin; p.seed = h.seed;
+  const bool whole = h.crop_x == 0 && h.crop_y == 0 && h.crop_w == s->width && h.crop_h == s->height;
+  if (!whole) { p.crop_x = h.crop_x; p.crop_y = h.crop_y; p.crop_w = h.crop_w; p.crop_h = h.crop_h; }
+  LrFilm* f = nullptr;
+  if ((rc = film_alloc(s, &p, h.has_sumsq, &f)) != LR_OK) return rc;
+  const size_t n = (size_t)h.crop_w * h.crop_h * 3;
+  cudaError_t e = cudaMemcpy(f->d_sum, host.data(), n * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && h.has_sumsq) e = cudaMemcpy(f->d_sumsq, host.data() + n, n * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { lr_film_destroy(f); return fail(LR_ERR_CUDA, std::string("film load: ") + cudaGetErrorString(e)); }
+  f->spp_done = h.spp_done;
+  *out = f;
+  return LR_OK;
+}
+int lr_film_load(const LrScene* s, const char* path, LrFilm** out) { LR_GUARDED(film_load_body(s, path, out)); }
 
 static int measure_read(uint64_t bytes, int iters, int warm, float* gbs) {
   if (!gbs || bytes < (1u << 20) || iters <= 0) return fail(LR_ERR_INVALID, "bad argument");

@@ -7,6 +7,10 @@
 // Extra, optional arguments (not in the reference):  --spp N  --resolution WxH  --seed S  --device D
 //   --gpus N (render on devices D..D+N-1 of this box from this one process: lr_render_multi, samples sharded by index)
 //   --assets DIR (root that mesh/IBL paths are resolved against; default: the current directory, like the reference)
+//   --progress N (render N samples per pixel at a time through an LrFilm and print the progress line main.rs:81-91 left
+//   commented out)  --checkpoint FILE (with --progress: the film is saved after every chunk, and an existing FILE is
+//   resumed — bit for bit the image of an uninterrupted run)  --aov normal|depth (Scene::normal / Scene::depth,
+//   scene.rs:48-62, instead of the radiance; depth is written normalised to its maximum)
 #include <sys/stat.h>
 
 #include <chrono>
@@ -38,7 +42,9 @@ int main(int argc, char** argv) {
   std::printf("start: %s\n", stamp("%Y-%m-%dT%H:%M:%S%z").c_str());
   const char* scene_path = nullptr;
   const char* assets = nullptr;
-  int spp = -1, ow = 0, oh = 0, device = 0, gpus = 1;
+  const char* checkpoint = nullptr;
+  const char* aov = nullptr;
+  int spp = -1, ow = 0, oh = 0, device = 0, gpus = 1, progress = 0;
   unsigned long long seed = 0;
   for (int i = 1; i < argc; i++) {
     const std::string a = argv[i];
@@ -52,10 +58,16 @@ int main(int argc, char** argv) {
     else if (a == "--device") device = std::atoi(need("--device"));
     else if (a == "--gpus") gpus = std::atoi(need("--gpus"));
     else if (a == "--assets") assets = need("--assets");
+    else if (a == "--progress") progress = std::atoi(need("--progress"));
+    else if (a == "--checkpoint") checkpoint = need("--checkpoint");
+    else if (a == "--aov") aov = need("--aov");
     else if (!scene_path) scene_path = argv[i];
     else { std::fprintf(stderr, "error: unexpected argument `%s`\n", argv[i]); return 2; }
   }
   if (!scene_path) { std::fprintf(stderr, "Path for .toml must be specified.\n"); return 2; }   // main.rs:47-49
+  if (aov && std::strcmp(aov, "normal") != 0 && std::strcmp(aov, "depth") != 0) { std::fprintf(stderr, "error: --aov normal|depth\n"); return 2; }
+  if (checkpoint && progress <= 0) { std::fprintf(stderr, "error: --checkpoint needs --progress N\n"); return 2; }
+  if ((progress > 0 || aov) && gpus > 1) { std::fprintf(stderr, "error: --progress / --aov render on one GPU\n"); return 2; }
   std::printf("loading: %s\n", scene_path);
 
   LrHostScene* hs = nullptr;
@@ -88,8 +100,45 @@ int main(int argc, char** argv) {
     for (int i = 0; i < gpus; i++) devices[i] = device + i;
     std::printf("gpus: %d (devices %d..%d, samples sharded by index, one peer-reading reduce)\n", gpus, device, device + gpus - 1);
     if (lr_render_multi(lr_host_scene_desc(hs), &p, gpus, devices, img.data(), nullptr, &st) != LR_OK) return die("rendering");
+  } else if (aov) {
+    std::memset(&st, 0, sizeof(st));
+    const bool normal = std::strcmp(aov, "normal") == 0;
+    std::vector<float> buf((size_t)cfg.width * cfg.height * (normal ? 3 : 1));
+    if (lr_render_aov(scene, &p, normal ? LR_AOV_NORMAL : LR_AOV_DEPTH, buf.data()) != LR_OK) return die("rendering the AOV");
+    if (normal) img = buf;
+    else {
+      float mx = 0.0f;
+      for (float v : buf) mx = v > mx ? v : mx;
+      for (size_t i = 0; i < buf.size(); i++) img[3 * i] = img[3 * i + 1] = img[3 * i + 2] = mx > 0.0f ? buf[i] / mx : 0.0f;
+    }
+    std::printf("aov: %s\n", aov);
+  } else if (progress > 0) {
+    // the progress hook of main.rs:81-91 (chunks of samples instead of pixels), resumable through a checkpoint file
+    p.splits = 1;                                             // samples are added in order: any cut of the range gives the same bits
+    LrFilm* film = nullptr;
+    struct stat sb;
+    if (checkpoint && stat(checkpoint, &sb) == 0) {
+      if (lr_film_load(scene, checkpoint, &film) != LR_OK) return die("resuming the checkpoint");
+    } else if (lr_film_create(scene, &p, 0, &film) != LR_OK) return die("creating the film");
+    int32_t done = 0;
+    lr_film_info(film, &done, nullptr, nullptr, nullptr);
+    if (done > 0) std::printf("resuming: %d of %d spp are in %s\n", done, cfg.samples, checkpoint);
+    std::memset(&st, 0, sizeof(st));
+    while (done < cfg.samples) {
+      const int n = cfg.samples - done < progress ? cfg.samples - done : progress;
+      LrStats part;
+      if (lr_film_render(film, n, &part) != LR_OK) return die("rendering");
+      done += n;
+      st.kernel_ms += part.kernel_ms; st.samples += part.samples; st.rays += part.rays; st.nonfinite_samples += part.nonfinite_samples;
+      if (checkpoint && lr_film_save(film, checkpoint) != LR_OK) return die("writing the checkpoint");
+      std::printf("\rprocessing... (%d/%d : %.0f%%) ", done, cfg.samples, 100.0 * done / cfg.samples);
+      std::fflush(stdout);
+    }
+    std::printf("\n");
+    if (lr_film_read(film, img.data(), nullptr) != LR_OK) return die("reading the film");
+    lr_film_destroy(film);
   } else if (lr_render(scene, &p, img.data(), nullptr, &st) != LR_OK) return die("rendering");
-  std::printf("render: %.3f ms on the GPU, %.1f Msamples/s, %.1f Mrays/s, %llu non-finite samples\n", st.kernel_ms,
+  if (!aov) std::printf("render: %.3f ms on the GPU, %.1f Msamples/s, %.1f Mrays/s, %llu non-finite samples\n", st.kernel_ms,
               st.samples / (st.kernel_ms * 1e3), st.rays / (st.kernel_ms * 1e3), (unsigned long long)st.nonfinite_samples);
 
   std::printf("\nsaving...\n");

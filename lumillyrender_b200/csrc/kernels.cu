@@ -80,6 +80,43 @@ rays_kernel(const __grid_constant__ DevScene sc, long long n, const float* __res
   }
 }
 
+// AOVs: Scene::normal / Scene::depth (scene.rs:48-62) of the camera ray of every sample of the range — the SAME camera rays
+// the render draws (same counter-based stream, camera draws first) — averaged per pixel in sample order.
+//   normal: hit ? n / 2 + (0.5, 0.5, 0.5) : (0, 0, 0)   (3 floats per pixel)      depth: hit ? distance : 0   (1 float per pixel)
+__global__ void __launch_bounds__(kBlockThreads)
+aov_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ DevParams p, int kind, float* __restrict__ out) {
+  const long long gid = (long long)blockIdx.x * kBlockThreads + threadIdx.x;
+  const long long tile = gid >> 5;
+  const int lane = (int)(gid & 31);
+  if (tile >= (long long)p.tiles_x * p.tiles_y) return;
+  const int lx = (int)(tile % p.tiles_x) * 8 + (lane & 7), ly = (int)(tile / p.tiles_x) * 4 + (lane >> 3);
+  if (lx >= p.crop_w || ly >= p.crop_h) return;
+  const int x = p.crop_x + lx, y = p.crop_y + ly;
+  const unsigned int pixel = (unsigned int)(y * sc.cam.width + x);
+  F3 sum = f3(0.0f, 0.0f, 0.0f);
+  for (int si = 0; si < p.spp_count; si++) {
+    Pcg rng;
+    rng.seed(p.seed, pixel, (unsigned int)(p.spp_begin + si));
+    F3 o, d;
+    float g, w;
+    camera_sample(sc.cam, x, y, [&]() { return rng.next(); }, o, d, g, w);
+    float t;
+    int id;
+    TraceCounters tc;
+    trace<false>(sc, o, d, t, id, tc);
+    F3 v = f3(0.0f, 0.0f, 0.0f);
+    if (id != -1) {
+      if (kind == LR_AOV_NORMAL) v = surface_at(sc, o, d, t, id).n / 2.0f + f3(0.5f, 0.5f, 0.5f);   // scene.rs:52
+      else v = f3(t, 0.0f, 0.0f);                                                                    // scene.rs:60
+    }
+    sum = sum + v;
+  }
+  const size_t i = (size_t)ly * p.crop_w + lx;
+  const float n = (float)p.spp_count;
+  if (kind == LR_AOV_NORMAL) { out[3 * i] = sum.x / n; out[3 * i + 1] = sum.y / n; out[3 * i + 2] = sum.z / n; }
+  else out[i] = sum.x / n;
+}
+
 // bandwidth microbenchmark: every thread streams 128-bit loads over a working set `n4` float4s,
 // `iters` passes.  With a working set << 126 MB it measures the L2 read peak, >> 126 MB the HBM read peak.
 __global__ void __launch_bounds__(256) read_bw_kernel(const float4* __restrict__ buf, size_t n4, int iters, float* __restrict__ sink) {
@@ -136,6 +173,12 @@ cudaError_t launch_primary(const DevScene& sc, float u, float v, float ua, float
   const int tiles_x = (sc.cam.width + 7) / 8, tiles_y = (sc.cam.height + 3) / 4;
   const long long threads = (long long)tiles_x * tiles_y * 32;
   primary_kernel<<<(unsigned int)((threads + kBlockThreads - 1) / kBlockThreads), kBlockThreads, 0, stream>>>(sc, tiles_x, tiles_y, u, v, ua, va, prim, t);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_aov(const DevScene& sc, const DevParams& p, int kind, float* out, cudaStream_t stream) {
+  const long long threads = (long long)p.tiles_x * p.tiles_y * 32;
+  aov_kernel<<<(unsigned int)((threads + kBlockThreads - 1) / kBlockThreads), kBlockThreads, 0, stream>>>(sc, p, kind, out);
   return cudaGetLastError();
 }
 

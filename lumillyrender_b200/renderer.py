@@ -152,6 +152,23 @@ class Scene:
         check(self._lib.lr_stats_fetch(self._s, C.c_void_p(int(stream)) if stream else None, C.byref(st)))
         return st.as_dict()
 
+    def render_aov(self, kind, **kw):
+        """`Scene::normal` / `Scene::depth` (scene.rs:48-62) of the camera rays of the sample range, averaged per pixel:
+        kind "normal" -> HxWx3 (hit ? n/2 + 0.5 : 0), "depth" -> HxW (hit ? distance : 0)."""
+        p = kw.pop("params", None) or self.params(**kw)
+        k = {"normal": capi.LR_AOV_NORMAL, "depth": capi.LR_AOV_DEPTH}[kind] if isinstance(kind, str) else int(kind)
+        shape = self._shape(p) if k == capi.LR_AOV_NORMAL else self._shape(p)[:2]
+        out = np.empty(shape, dtype=np.float32)
+        check(self._lib.lr_render_aov(self._s, C.byref(p), k, _fptr(out)))
+        return out
+
+    def film(self, sumsq=False, **kw):
+        """A resumable render of this scene (the progress hook the reference abandoned, main.rs:81-91): see Film."""
+        return Film(self, params=kw.pop("params", None) or self.params(**kw), sumsq=sumsq)
+
+    def load_film(self, path):
+        return Film(self, path=path)
+
     def trace_primary(self, u=0.5, v=0.5, ua=0.5, va=0.5):
         prim = np.empty((self.height, self.width), dtype=np.int32)
         t = np.empty((self.height, self.width), dtype=np.float32)
@@ -172,6 +189,57 @@ class Scene:
         if self._s:
             self._lib.lr_scene_destroy(self._s)
             self._s = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Film:
+    """Per-pixel sums of a render in progress on the scene's device (lr_film_*): `render(n)` adds the next n sample
+    indices, `read()` gives the mean so far, `save(path)` / `Scene.load_film(path)` checkpoint and resume.  With
+    splits = 1 any cut of the sample range into `render` calls gives bit for bit the image of one `Scene.render`."""
+
+    def __init__(self, scene, params=None, sumsq=False, path=None):
+        self._lib = capi.load_library()
+        self.scene = scene
+        self._f = C.c_void_p()
+        if path is not None:
+            check(self._lib.lr_film_load(scene._s, str(path).encode(), C.byref(self._f)))
+        else:
+            check(self._lib.lr_film_create(scene._s, C.byref(params), 1 if sumsq else 0, C.byref(self._f)))
+        _, w, h, self.has_sumsq = self._info()
+        self._shape = (h, w, 3)
+
+    def _info(self):
+        v = [C.c_int32() for _ in range(4)]
+        check(self._lib.lr_film_info(self._f, *[C.byref(x) for x in v]))
+        return [x.value for x in v]
+
+    @property
+    def spp(self):
+        return self._info()[0]
+
+    def render(self, spp):
+        st = LrStats()
+        check(self._lib.lr_film_render(self._f, int(spp), C.byref(st)))
+        return st.as_dict()
+
+    def read(self, sumsq=False):
+        img = np.empty(self._shape, dtype=np.float32)
+        sq = np.empty(self._shape, dtype=np.float32) if sumsq else None
+        check(self._lib.lr_film_read(self._f, _fptr(img), _fptr(sq) if sumsq else None))
+        return (img, sq) if sumsq else img
+
+    def save(self, path):
+        check(self._lib.lr_film_save(self._f, str(path).encode()))
+
+    def close(self):
+        if self._f:
+            self._lib.lr_film_destroy(self._f)
+            self._f = C.c_void_p()
 
     def __del__(self):
         try:

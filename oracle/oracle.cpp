@@ -1051,6 +1051,52 @@ int orc_render(const OrcScene* s, const LrRenderParams* p, int traversal, int rn
   return LR_OK;
 }
 
+// Scene::normal / Scene::depth (scene.rs:48-62) over the camera rays of the sample range, averaged per pixel in sample
+// order.  The reference defines the two functions but main.rs never calls them; the driver loop here is main.rs:92-104
+// with the AOV in place of the radiance (no g_term / pdf weight: an AOV is not a radiance).  Streams: the counter-based
+// one shared with the device (math_mode 1: the lens cameras' aperture sample uses the specified sincos).
+int orc_render_aov(const OrcScene* s, const LrRenderParams* p, int kind, int traversal, int n_threads, float* out) {
+  if (!s || !p || !out || p->spp_count <= 0) return LR_ERR_INVALID;
+  const SceneImpl& sc = s->impl;
+  const int W = sc.camera.width, H = sc.camera.height;
+  const int cx = p->crop_w > 0 ? p->crop_x : 0, cy = p->crop_w > 0 ? p->crop_y : 0;
+  const int cw = p->crop_w > 0 ? p->crop_w : W, ch = p->crop_w > 0 ? p->crop_h : H;
+  if (cx < 0 || cy < 0 || cx + cw > W || cy + ch > H) return LR_ERR_INVALID;
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  std::atomic<int> next_row{0};
+  auto worker = [&]() {
+    g_math_mode = 1;
+    Rng rng;
+    Tracer tr{sc, traversal, Counters{}};
+    while (true) {
+      const int ly = next_row.fetch_add(1);
+      if (ly >= ch) break;
+      for (int lx = 0; lx < cw; lx++) {
+        const int x = cx + lx, y = cy + ly;
+        const uint32_t pixel = (uint32_t)(y * W + x);
+        V3 sum = v3(0, 0, 0);
+        for (int si = 0; si < p->spp_count; si++) {
+          rng.seed_counter(p->seed, pixel, (uint32_t)(p->spp_begin + si));
+          const CamSample cs = camera_sample(sc.camera, x, y, [&]() { return rng.next(); });
+          Intersection it;
+          V3 v = v3(0, 0, 0);                                                     // None => Vector3::zero() / 0.0
+          if (tr.intersect(cs.ray, it)) v = kind == 0 ? it.normal / 2.0f + v3(0.5f, 0.5f, 0.5f)   // scene.rs:52
+                                                      : v3(it.distance, 0, 0);                    // scene.rs:60
+          sum = sum + v;
+        }
+        const size_t i = (size_t)ly * cw + lx;
+        const float n = (float)p->spp_count;
+        if (kind == 0) { out[3 * i] = sum.x / n; out[3 * i + 1] = sum.y / n; out[3 * i + 2] = sum.z / n; }
+        else out[i] = sum.x / n;
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int k = 0; k < n_threads; k++) th.emplace_back(worker);
+  for (auto& k : th) k.join();
+  return LR_OK;
+}
+
 int orc_trace_primary(const OrcScene* s, float u, float v, float ua, float va, int traversal, int n_threads,
                       int32_t* prim, float* t) {
   if (!s || !prim || !t) return LR_ERR_INVALID;

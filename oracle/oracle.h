@@ -47,6 +47,10 @@ int orc_render(const OrcScene* s, const LrRenderParams* p, int traversal, int rn
 void orc_set_math_mode(int mode);     /* for the calling thread (unit-level entry points) */
 void orc_spec_sincos(float x, float* s, float* c);
 
+/* Scene::normal (kind 0, 3 floats per pixel) / Scene::depth (kind 1, 1 float per pixel), scene.rs:48-62, of the
+ * camera rays of the sample range, averaged per pixel in sample order (shared counter-based stream). */
+int orc_render_aov(const OrcScene* s, const LrRenderParams* p, int kind, int traversal, int n_threads, float* out);
+
 int orc_trace_primary(const OrcScene* s, float u, float v, float ua, float va, int traversal,
                       int n_threads, int32_t* prim, float* t);
 int orc_trace_rays(const OrcScene* s, int64_t n, const float* origins, const float* directions,

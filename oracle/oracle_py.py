@@ -46,6 +46,7 @@ def lib():
         L.orc_scene_destroy.argtypes = [C.c_void_p]
         L.orc_scene_nodes.argtypes = [C.c_void_p]
         L.orc_render.argtypes = [C.c_void_p, C.POINTER(LrRenderParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _PF, _PF, C.POINTER(OrcStats)]
+        L.orc_render_aov.argtypes = [C.c_void_p, C.POINTER(LrRenderParams), C.c_int, C.c_int, C.c_int, _PF]
         L.orc_set_math_mode.argtypes = [C.c_int]
         L.orc_spec_sincos.argtypes = [C.c_float, _PF, _PF]
         L.orc_trace_primary.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _PI, _PF]
@@ -124,6 +125,17 @@ class OracleScene:
         if rc != 0:
             raise RuntimeError("orc_render failed: %d" % rc)
         return out, sq, st.as_dict()
+
+    def render_aov(self, params, kind, traversal=0, threads=0):
+        """Scene::normal ("normal": HxWx3) / Scene::depth ("depth": HxW) averaged over the camera rays of the sample range."""
+        h = params.crop_h if params.crop_w > 0 else self.height
+        w = params.crop_w if params.crop_w > 0 else self.width
+        k = {"normal": 0, "depth": 1}[kind]
+        out = np.zeros((h, w, 3) if k == 0 else (h, w), dtype=np.float32)
+        rc = self._L.orc_render_aov(self._s, C.byref(params), k, traversal, threads, fp(out))
+        if rc != 0:
+            raise RuntimeError("orc_render_aov failed: %d" % rc)
+        return out
 
     def trace_primary(self, u=0.5, v=0.5, ua=0.5, va=0.5, traversal=0, threads=0):
         prim = np.empty((self.height, self.width), dtype=np.int32)

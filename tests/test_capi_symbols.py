@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(lr):
     out = subprocess.run(["nm", "-D", "--defined-only", lr.library_path()], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (lr_[a-z0-9_]+)", out))
     assert set(names) <= exported
-    assert lib.lr_abi_version() == 2
+    assert lib.lr_abi_version() == 3
 
 
 def test_sass_is_sm100a_only(lr):

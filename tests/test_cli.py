@@ -31,6 +31,8 @@ def test_bad_flags_exit_2(cli):
     assert run(cli, "--spp").returncode == 2
     assert run(cli, "scenes/primitive.toml", "--resolution", "banana").returncode == 2
     assert run(cli, "scenes/primitive.toml", "extra.toml").returncode == 2
+    assert run(cli, "scenes/primitive.toml", "--aov", "albedo").returncode == 2
+    assert run(cli, "scenes/primitive.toml", "--checkpoint", "x.ck").returncode == 2          # needs --progress
 
 
 def test_missing_scene_file_is_an_error_not_a_crash(cli):
@@ -57,3 +59,35 @@ def test_cli_renders_and_writes_the_image(cli, tmp_path):
         assert line in r.stdout, line
     files = os.listdir(os.path.join(str(tmp_path), "images"))
     assert len(files) == 1 and files[0].startswith("image_") and files[0].endswith("_4.png")   # main.rs:147-169
+
+
+@pytest.mark.gpu
+def test_cli_progress_checkpoint_resume_and_aov(cli, tmp_path):
+    """--progress renders in chunks through an LrFilm and prints the reference's abandoned progress line (main.rs:81-91);
+    an interrupted run (here: a first run asked for 4 of the 8 spp) resumed from its checkpoint writes byte for byte the
+    PNG of an uninterrupted one; --aov writes Scene::normal / Scene::depth (scene.rs:48-62)."""
+    scene = os.path.join(ROOT, "scenes", "primitive.toml")
+    common = ("--resolution", "64x64", "--assets", ROOT, "--seed", "3")
+
+    def png(d):
+        files = sorted(os.listdir(os.path.join(d, "images")))
+        with open(os.path.join(d, "images", files[-1]), "rb") as f:
+            return f.read()
+    a, b = tmp_path / "a", tmp_path / "b"
+    a.mkdir(); b.mkdir()
+    r = run(cli, scene, "--spp", "8", "--progress", "3", *common, cwd=str(a))
+    assert r.returncode == 0 and "processing... (8/8 : 100%)" in r.stdout, r.stderr
+    ck = str(b / "film.ck")
+    r = run(cli, scene, "--spp", "4", "--progress", "4", "--checkpoint", ck, *common, cwd=str(b))
+    assert r.returncode == 0 and os.path.exists(ck), r.stderr
+    for f in os.listdir(str(b / "images")):
+        os.remove(str(b / "images" / f))
+    r = run(cli, scene, "--spp", "8", "--progress", "2", "--checkpoint", ck, *common, cwd=str(b))
+    assert r.returncode == 0 and "resuming: 4 of 8 spp" in r.stdout, r.stderr
+    assert png(str(a)) == png(str(b))
+    for kind in ("normal", "depth"):
+        c = tmp_path / kind
+        c.mkdir()
+        r = run(cli, scene, "--spp", "2", "--aov", kind, *common, cwd=str(c))
+        assert r.returncode == 0 and ("aov: " + kind) in r.stdout, r.stderr
+        assert len(png(str(c))) > 100

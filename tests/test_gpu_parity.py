@@ -396,3 +396,101 @@ def test_full_size_properties(lr, assets, gpu):
     crop, _, _ = s.render(spp=4, seed=21, crop=(901, 333, 257, 129))
     assert np.array_equal(crop, full[333:333 + 129, 901:901 + 257])
     assert 0.2 < float(full.mean()) < 0.6 and st["rays"] > 4 * 1920 * 1370 * 3
+
+
+@pytest.mark.parametrize("name", ["primitive", "sample", "welcome-2018", "vr"])
+def test_aovs_match_oracle(scenes, lr, name):
+    """Scene::normal / Scene::depth (scene.rs:48-62) over the camera rays of a sample range: the CUDA path against the
+    oracle, bit for bit on pixels whose samples all hit the same primitives (every operation is an exact-rounded fp32 one
+    applied in the same order; the lens / omnidirectional cameras go through the specified sincos on both sides)."""
+    d, s, o = scenes(name)
+    for kw in (dict(spp=1, seed=3), dict(spp=5, spp_begin=2, seed=9, crop=(31, 17, 64, 48))):
+        p = make_params(lr, d.config, **kw)
+        for kind in ("normal", "depth"):
+            g = s.render_aov(kind, params=p)
+            r = o.render_aov(p, kind)
+            assert g.shape == r.shape
+            same = (g == r).mean()
+            print("%s %s %s: bit-equal on %.6f of the values" % (name, kind, kw, same))
+            assert same >= 0.9999 and np.allclose(g, r, rtol=1e-5, atol=1e-6)
+    # the AOV of sample 0 with a fixed jitter is the primary probe
+    depth = s.render_aov("depth", spp=1, seed=3)
+    normal = s.render_aov("normal", spp=1, seed=3)
+    assert ((depth > 0) == (normal != 0).any(-1)).all()
+    hit = depth > 0
+    assert np.allclose(np.linalg.norm(normal[hit] * 2 - 1, axis=-1), 1.0, atol=1e-5)
+
+
+def test_aov_error_paths(scenes, lr):
+    from lumillyrender_b200.capi import LumillyError
+    d, s, o = scenes("primitive")
+    with pytest.raises(LumillyError):
+        s.render_aov(7, spp=1)
+    with pytest.raises(LumillyError):
+        s.render_aov("depth", spp=0)
+
+
+@pytest.mark.parametrize("name", ["new-cbox", "sample", "welcome-2018"])
+def test_resumable_render_equals_one_pass_bit_for_bit(scenes, lr, name, tmp_path):
+    """Progressive / resumable rendering (the hook main.rs:81-91 abandoned): a film rendered as [0,3) + [3,4) + [4,9) — with a
+    checkpoint written to disk and restored into a NEW film in between — is bit for bit the image (and sum of squares,
+    and ray count) of one lr_render over [0,9): with splits = 1 every pixel's samples are added in sample order starting
+    from the stored sum, the fold of main.rs:92-104."""
+    d, s, o = scenes(name)
+    ref, ref_sq, st = s.render(spp=9, seed=21, splits=1, sumsq=True)
+    film = s.film(sumsq=True, seed=21, splits=1)
+    rays = film.render(3)["rays"]
+    assert film.spp == 3
+    part = film.read()
+    first, _, _ = s.render(spp=3, seed=21, splits=1)
+    assert np.array_equal(part, first, equal_nan=True)
+    rays += film.render(1)["rays"]
+    ck = str(tmp_path / "film.ck")
+    film.save(ck)
+    film.close()
+    resumed = s.load_film(ck)
+    assert resumed.spp == 4 and resumed.has_sumsq
+    rays += resumed.render(5)["rays"]
+    img, sq = resumed.read(sumsq=True)
+    assert resumed.spp == 9 and rays == st["rays"]
+    assert np.array_equal(img, ref, equal_nan=True) and np.array_equal(sq, ref_sq, equal_nan=True)
+    # a crop film resumes the same way
+    crop = (8, 4, 40, 24)
+    cf = s.film(seed=21, splits=1, crop=crop)
+    cf.render(4)
+    cf.save(ck)
+    cf2 = s.load_film(ck)
+    cf2.render(5)
+    assert np.array_equal(cf2.read(), ref[4:28, 8:48], equal_nan=True)
+
+
+def test_film_error_paths(scenes, lr, tmp_path):
+    from lumillyrender_b200.capi import LumillyError
+    d, s, o = scenes("new-cbox")
+    film = s.film(seed=1, splits=1)
+    with pytest.raises(LumillyError):
+        film.read()                                   # no samples yet
+    with pytest.raises(LumillyError):
+        film.render(0)
+    film.render(1)
+    with pytest.raises(LumillyError):
+        film.read(sumsq=True)                         # created without sums of squares
+    with pytest.raises(LumillyError) as e:
+        s.load_film(str(tmp_path / "absent.ck"))
+    assert e.value.code == -4
+    bad = tmp_path / "bad.ck"
+    bad.write_bytes(b"not a film checkpoint at all" * 8)
+    with pytest.raises(LumillyError) as e:
+        s.load_film(str(bad))
+    assert e.value.code == -5
+    ck = str(tmp_path / "f.ck")
+    film.save(ck)
+    with open(ck, "rb") as f:
+        data = f.read()
+    (tmp_path / "short.ck").write_bytes(data[:len(data) // 2])
+    with pytest.raises(LumillyError) as e:
+        s.load_film(str(tmp_path / "short.ck"))
+    assert e.value.code == -5
+    d2, s2, _ = scenes("primitive")                    # another film resolution
+    with pytest.raises(LumillyError):
+        s2.load_film(ck)

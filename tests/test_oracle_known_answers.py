@@ -720,3 +720,39 @@ def test_glass_sphere_in_a_white_furnace_is_invisible(lr, orc, ior):
     s, _, st = o.render(make_params(lr, d.config, integrator=0, spp=spp, seed=4, depth=5, depth_limit=64, no_direct_emitter=0), traversal=0)
     assert st["nonfinite_samples"] == 0 and st["rays"] > 1.5 * st["samples"]
     assert np.allclose(s / spp, 1.0, atol=3e-6), (float((s / spp).min()), float((s / spp).max()))
+
+
+def test_aovs_known_answers(lr, orc):
+    """Scene::normal / Scene::depth (scene.rs:48-62) by hand: a unit sphere at the origin seen from (0, 0, 5) through an ideal
+    pinhole.  Centre pixel: distance 4, normal (0, 0, 1) -> encoded (0.5, 0.5, 1); a corner pixel misses -> zeros; on the
+    sphere the decoded normal is the unit vector from the centre to the hit point o + t d, whatever the jitter."""
+    from lumillyrender_b200 import capi
+    from conftest import make_params
+    mats = (capi.LrMaterial * 1)()
+    mats[0].color[:] = [0.5, 0.5, 0.5]
+    S = (capi.LrSphere * 1)()
+    S[0].center[:] = [0, 0, 0]; S[0].radius = 1.0; S[0].material = 0; S[0].prim_id = 0
+    m = (C.c_float * 16)()
+    L = capi.load_library()
+    L.lr_matrix_look_at((C.c_float * 3)(0, 0, 5), (C.c_float * 3)(0, 0, 0), (C.c_float * 3)(0, 1, 0), m)
+    cam = capi.LrCamera()
+    L.lr_camera_ideal_pinhole(m, 40.0, 33, 33, C.byref(cam))
+    d = lr.Description.from_arrays(mats, (capi.LrTriangle * 0)(), S, cam)
+    o = orc.OracleScene(d.desc, keepalive=d)
+    p = make_params(lr, d.config, spp=4, seed=1)
+    depth, normal = o.render_aov(p, "depth"), o.render_aov(p, "normal")
+    assert depth.shape == (33, 33) and normal.shape == (33, 33, 3)
+    assert abs(depth[16, 16] - 4.0) < 2e-3 and np.allclose(normal[16, 16], [0.5, 0.5, 1.0], atol=2e-2)
+    assert depth[0, 0] == 0.0 and (normal[0, 0] == 0.0).all()
+    assert ((depth > 0) == (normal != 0).any(-1)).all()
+    # one sample: decode the normal and compare with the geometry of the hit
+    p1 = make_params(lr, d.config, spp=1, seed=1)
+    depth, normal = o.render_aov(p1, "depth"), o.render_aov(p1, "normal")
+    hit = depth > 0
+    n = normal[hit] * 2 - 1
+    assert np.allclose(np.linalg.norm(n, axis=-1), 1.0, atol=1e-5)
+    # |o + t d - c| = 1 and the hit lies along n: o + t d = n  =>  t = |n - o| with o = (0, 0, 5)
+    assert np.allclose(np.linalg.norm(n - np.array([0, 0, 5.0]), axis=-1), depth[hit], atol=1e-4)
+    # sample ranges compose: mean over [0,4) = mean of the four single-sample AOVs
+    singles = [o.render_aov(make_params(lr, d.config, spp=1, spp_begin=k, seed=1), "depth") for k in range(4)]
+    assert np.allclose(o.render_aov(p, "depth"), np.mean(singles, axis=0), rtol=1e-6, atol=1e-7)

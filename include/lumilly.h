@@ -269,8 +269,18 @@ typedef struct LrSceneConfig {            /* [renderer] + [film] of the TOML    
   int32_t output;                         /* 0 = png, 1 = hdr                          */
   float gamma;
   int32_t n_prims, n_emitters;
-  float bvh_build_seconds;
+  float bvh_build_seconds;                /* host triangles -> host node array, whichever builder ran */
+  int32_t bvh_builder;                    /* LrBvhBuilder that built the tree                          */
+  float bvh_device_kernel_ms;             /* LR_BVH_DEVICE: CUDA-event time of the build kernels alone */
 } LrSceneConfig;
+
+/* Who builds the BVH (replaces BVH::new, src/bvh.rs:57-127; the nearest hit does not depend on the tree's topology):
+ * LR_BVH_HOST   binned SAH on the host's cores — the better tree, seconds for a million triangles;
+ * LR_BVH_DEVICE Morton-order radix tree (LBVH) built by CUDA kernels — milliseconds; needs a CUDA device.
+ * lr_host_scene_load uses LR_BVH_HOST unless the environment says LR_BVH_BUILDER=device.                       */
+typedef enum LrBvhBuilder { LR_BVH_HOST = 0, LR_BVH_DEVICE = 1 } LrBvhBuilder;
+/* rebuilds the scene's BVH with the given builder (the LrSceneDesc pointer stays valid, its arrays are replaced) */
+int lr_host_scene_rebuild_bvh(LrHostScene* hs, int32_t builder);
 
 /* Parses `toml_path` (mesh/IBL paths resolved against asset_root, or the CWD if NULL — the
  * reference resolves against the CWD, description.rs:155, sky.rs:44).  width/height > 0

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblumilly_b200.so")
 CLI = os.path.join(HERE, "bin", "lumilly")
-SOURCES = ["kernels.cu", "api.cpp", "bvh_build.cpp", "toml_obj.cpp", "host_scene.cpp", "image_io.cpp"]
+SOURCES = ["kernels.cu", "api.cpp", "bvh_build.cpp", "bvh_build_gpu.cu", "toml_obj.cpp", "host_scene.cpp", "image_io.cpp"]
 HEADERS = ["device_scene.h", "device_path.cuh", "persistent.cuh", "pool.cuh", "path_vertex.inc", "kernels.h", "common.h", "host_scene.h", "../../include/lumilly.h"]
 
 

@@ -16,6 +16,7 @@ LR_CAM_IDEAL_PINHOLE, LR_CAM_PINHOLE, LR_CAM_THIN_LENS, LR_CAM_OMNIDIRECTIONAL =
 LR_SKY_UNIFORM, LR_SKY_IBL = 0, 1
 LR_INTEGRATOR_PT, LR_INTEGRATOR_PT_DIRECT = 0, 1
 LR_AOV_NORMAL, LR_AOV_DEPTH = 0, 1
+LR_BVH_HOST, LR_BVH_DEVICE = 0, 1
 
 f32, i32, u64, i64 = C.c_float, C.c_int32, C.c_uint64, C.c_int64
 
@@ -70,7 +71,7 @@ class LrStats(C.Structure):
 class LrSceneConfig(C.Structure):
     _fields_ = [("samples", i32), ("depth", i32), ("depth_limit", i32), ("no_direct_emitter", i32), ("threads", i32),
                 ("integrator", i32), ("width", i32), ("height", i32), ("output", i32), ("gamma", f32), ("n_prims", i32),
-                ("n_emitters", i32), ("bvh_build_seconds", f32)]
+                ("n_emitters", i32), ("bvh_build_seconds", f32), ("bvh_builder", i32), ("bvh_device_kernel_ms", f32)]
 
 
 class LumillyError(RuntimeError):
@@ -115,6 +116,7 @@ SIGNATURES = {
     "lr_host_scene_desc": (C.POINTER(LrSceneDesc), [_VP]),
     "lr_host_scene_config": (C.c_int, [_VP, C.POINTER(LrSceneConfig)]),
     "lr_host_scene_free": (None, [_VP]),
+    "lr_host_scene_rebuild_bvh": (C.c_int, [_VP, i32]),
     "lr_host_scene_from_arrays": (C.c_int, [C.POINTER(LrMaterial), i32, C.POINTER(LrTriangle), i32, C.POINTER(LrSphere), i32,
                                             C.POINTER(LrCamera), C.POINTER(LrSky), C.POINTER(_VP)]),
     "lr_camera_ideal_pinhole": (C.c_int, [_PF, f32, i32, i32, C.POINTER(LrCamera)]),

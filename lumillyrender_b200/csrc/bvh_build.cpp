@@ -214,7 +214,10 @@ struct Builder {
 
 }  // namespace
 
-int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, int& depth_out, float& seconds_out, int& n_flat_out, float origin_extent) {
+int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, int& depth_out, float& seconds_out, int& n_flat_out,
+              float origin_extent, int builder, int* builder_used, float* device_kernel_ms) {
+  if (builder_used) *builder_used = LR_BVH_HOST;
+  if (device_kernel_ms) *device_kernel_ms = 0.0f;
   const auto t0 = std::chrono::steady_clock::now();
   if (const char* e = std::getenv("LR_LEAF_TARGET")) kLeafTarget = std::max(1, std::min(8, std::atoi(e)));
   nodes_out.clear();
@@ -261,6 +264,25 @@ int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, 
   }
   const int n = n_all - n_flat_out;                        // triangles that go into the tree: tris[0, n)
   if (n == 0) { seconds_out = std::chrono::duration<float>(std::chrono::steady_clock::now() - t0).count(); return LR_OK; }
+  if (builder == LR_BVH_DEVICE && n >= 1024) {
+    // the device builder: same flat list, same pad, same leaf target; a radix tree deeper than the traversal stack (only
+    // with tens of thousands of coincident centroids) goes to the host builder below instead
+    float extent = 0.0f;
+    for (int k = 0; k < 3; k++) extent = std::fmax(extent, std::fmax(std::fabs(scene.lo[k]), std::fabs(scene.hi[k])));
+    extent = std::fmax(extent, std::fmin(origin_extent, 1e30f));
+    float kernel_ms = 0.0f, sec = 0.0f;
+    std::vector<LrTriangle> work(tris);
+    if (int rc = build_bvh_device(work, n, 4e-6f * extent + 1e-30f, kLeafTarget, nodes_out, depth_out, sec, kernel_ms)) return rc;
+    if (depth_out < Builder::kStackGuardDepth) {
+      tris.swap(work);
+      if (builder_used) *builder_used = LR_BVH_DEVICE;
+      if (device_kernel_ms) *device_kernel_ms = kernel_ms;
+      seconds_out = std::chrono::duration<float>(std::chrono::steady_clock::now() - t0).count();
+      return LR_OK;
+    }
+    nodes_out.clear();
+    depth_out = 0;
+  }
   std::vector<Box> tri_box(n);
   std::vector<Vec3> centroid(n);
   std::vector<int> order(n);

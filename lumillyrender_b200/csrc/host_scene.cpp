@@ -3,6 +3,7 @@
 // description.rs (instances in TOML order, world-space triangles, camera selection).  Runs once
 // per scene; nothing here is on the per-sample path.  fp32 throughout, -ffp-contract=off.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -375,7 +376,7 @@ int LrHostScene::finalize() {
     origin_extent = std::fmax(origin_extent, std::fmax(std::fabs(desc.camera.position[k]), std::fabs(desc.camera.aperture_position[k])));
   for (const LrSphere& sp : spheres)
     for (int k = 0; k < 3; k++) origin_extent = std::fmax(origin_extent, std::fabs(sp.center[k]) + std::fmin(std::fabs(sp.radius), 16.0f * tri_extent));
-  if (int rc = build_bvh(triangles, nodes, depth, seconds, n_flat, origin_extent)) return rc;
+  if (int rc = build_bvh(triangles, nodes, depth, seconds, n_flat, origin_extent, bvh_builder, &bvh_builder_used, &bvh_device_kernel_ms)) return rc;
   desc.n_flat_triangles = n_flat;
   desc.materials = materials.data(); desc.n_materials = (int)materials.size();
   desc.triangles = triangles.data(); desc.n_triangles = (int)triangles.size();
@@ -385,6 +386,8 @@ int LrHostScene::finalize() {
   if (desc.sky.type == LR_SKY_IBL) desc.sky.pixels = sky_pixels.data();
   config.n_prims = desc.n_triangles + desc.n_spheres;
   config.bvh_build_seconds = seconds;
+  config.bvh_builder = bvh_builder_used;
+  config.bvh_device_kernel_ms = bvh_device_kernel_ms;
   int n_em = 0;
   auto emissive = [&](int m) {
     const LrMaterial& mm = materials[m];
@@ -402,6 +405,7 @@ int lr_host_scene_load(const char* toml_path, const char* asset_root, int32_t ow
   if (!toml_path || !out) return fail(LR_ERR_INVALID, "null argument");
   *out = nullptr;
   auto hs = std::make_unique<LrHostScene>();
+  if (const char* b = std::getenv("LR_BVH_BUILDER")) hs->bvh_builder = std::strcmp(b, "device") == 0 ? LR_BVH_DEVICE : LR_BVH_HOST;
   try {
     load_into(*hs, toml_path, asset_root ? asset_root : "", ow, oh);
   } catch (const LoadError& e) {
@@ -413,6 +417,21 @@ int lr_host_scene_load(const char* toml_path, const char* asset_root, int32_t ow
   *out = hs.release();
   return LR_OK;
 }
+
+static int lr_host_scene_rebuild_bvh_body(LrHostScene* hs, int32_t builder) {
+  if (!hs) return fail(LR_ERR_INVALID, "null argument");
+  if (builder != LR_BVH_HOST && builder != LR_BVH_DEVICE) return fail(LR_ERR_INVALID, "unknown BVH builder");
+  const int prev = hs->bvh_builder;
+  hs->bvh_builder = builder;
+  const int rc = hs->finalize();
+  if (rc == LR_OK) return rc;
+  // the scene keeps a valid tree: rebuild with the builder it had (the failed attempt cleared the node array)
+  const std::string msg = lr_last_error();
+  hs->bvh_builder = prev;
+  if (hs->finalize() != LR_OK) return rc;
+  return fail(rc, msg);
+}
+int lr_host_scene_rebuild_bvh(LrHostScene* hs, int32_t builder) { LR_GUARDED(lr_host_scene_rebuild_bvh_body(hs, builder)); }
 
 static int lr_host_scene_from_arrays_body(const LrMaterial* materials, int32_t n_materials, const LrTriangle* triangles, int32_t n_triangles,
                               const LrSphere* spheres, int32_t n_spheres, const LrCamera* camera, const LrSky* sky, LrHostScene** out) {

@@ -55,7 +55,13 @@ void camera_omnidirectional(const Mat4& m, int w, int h, LrCamera& out);
 void camera_pinhole(Vec3 position, Vec3 aperture_position, const float* sensor_size, int w, int h, float aperture_radius, LrCamera& out);
 
 // permutes `tris`: BVH leaf order first, then the `n_flat_out` large triangles kept outside the BVH
-int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, int& depth_out, float& seconds_out, int& n_flat_out, float origin_extent = 0.0f);
+// builder: LR_BVH_HOST = binned SAH on the host's cores (bvh_build.cpp), LR_BVH_DEVICE = Morton-order radix tree on the GPU
+// (bvh_build_gpu.cu; needs a CUDA device; falls back to the host builder for meshes of fewer than 1024 triangles or if the
+// radix tree comes out deeper than the device traversal stack)
+int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, int& depth_out, float& seconds_out, int& n_flat_out,
+              float origin_extent = 0.0f, int builder = 0, int* builder_used = nullptr, float* device_kernel_ms = nullptr);
+int build_bvh_device(std::vector<LrTriangle>& tris, int n_tree, float pad, int leaf_target, std::vector<LrBvhNode>& nodes_out, int& depth_out,
+                     float& seconds_out, float& kernel_ms_out);
 
 int load_hdr_file(const std::string& path, std::vector<float>& rgb, int& w, int& h);
 
@@ -70,5 +76,8 @@ struct LrHostScene {
   std::vector<float> sky_pixels;
   LrSceneDesc desc{};
   LrSceneConfig config{};
+  int bvh_builder = 0;        // LrBvhBuilder asked for (lr_host_scene_load: LR_BVH_BUILDER=device|host; lr_host_scene_rebuild_bvh)
+  int bvh_builder_used = 0;   // ... and the one that built the tree
+  float bvh_device_kernel_ms = 0.0f;
   int finalize();    // builds the BVH, counts emitters, fills desc
 };

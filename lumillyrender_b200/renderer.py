@@ -75,6 +75,14 @@ class Description:
     def desc(self):
         return self._lib.lr_host_scene_desc(self._h)
 
+    def rebuild_bvh(self, builder="device"):
+        """Rebuilds the BVH (BVH::new, bvh.rs:57-127): "host" = binned SAH on the host's cores, "device" = radix tree built
+        by CUDA kernels (needs a GPU).  Returns the build's wall seconds; `config` is refreshed."""
+        b = {"host": capi.LR_BVH_HOST, "device": capi.LR_BVH_DEVICE}[builder] if isinstance(builder, str) else int(builder)
+        check(self._lib.lr_host_scene_rebuild_bvh(self._h, b))
+        check(self._lib.lr_host_scene_config(self._h, C.byref(self.config)))
+        return self.config.bvh_build_seconds
+
     def camera(self):
         return self.desc.contents.camera
 

@@ -172,3 +172,48 @@ def test_statistical_parity_full_size_crop(full, lr, case):
     assert ok.mean() >= 0.999
     assert frac >= 0.99 and exact >= 0.99
     assert z <= 3.0
+
+
+@pytest.mark.parametrize("case", ["sample-144k", "welcome-1M"])
+def test_device_built_bvh_gives_the_same_hits_and_the_same_image(full, lr, case):
+    """The BVH built on the device (bvh_build_gpu.cu: Morton-order radix tree, replaces BVH::new, bvh.rs:57-127) against the
+    host's binned-SAH tree on the same scene.  The nearest hit is topology-independent (device_path.cuh), so EVERYTHING must
+    be bit-identical: primary hits over the whole film, 20k random rays (index, t, normal) and a rendered crop with its ray
+    count.  The build itself must take < 50 ms of kernel time at a million triangles."""
+    name, tris, res = CASES[case]
+    d, s, o = full(case)
+    host_nodes, host_depth = d.desc.contents.n_nodes, d.desc.contents.bvh_depth
+    pg, tg = s.trace_primary()
+    tri = _mesh_triangles(d)
+    rng = np.random.RandomState(7)
+    k = rng.randint(0, len(tri), 20000)
+    w = rng.dirichlet([1, 1, 1], 20000).astype(np.float32)
+    org = (tri[k] * w[:, :, None]).sum(1).astype(np.float32)
+    org[:10000] = np.array(list(d.camera().aperture_position), np.float32)
+    dirs = rng.normal(size=(20000, 3))
+    dirs[:10000] = tri[k[:10000], 0] - org[:10000]
+    dirs = (dirs / np.linalg.norm(dirs, axis=1, keepdims=True)).astype(np.float32)
+    ph, th, nh = s.trace_rays(org, dirs, normals=True)
+    x, y, _ = _window(_mesh_mask(pg), 128, 0.5)
+    img_h, _, st_h = s.render(spp=4, seed=3, splits=1, crop=(x, y, 128, 128))
+
+    d2 = d
+    sec = d2.rebuild_bvh("device")
+    cfg = d2.config
+    desc = d2.desc.contents
+    print("%s: device build %.1f ms wall (%.2f ms of kernels) for %d triangles -> %d nodes depth %d (host SAH: %d nodes depth %d)" % (
+        case, 1e3 * sec, cfg.bvh_device_kernel_ms, cfg.n_prims, desc.n_nodes, desc.bvh_depth, host_nodes, host_depth))
+    assert cfg.bvh_builder == 1 and desc.bvh_depth < 60
+    assert cfg.bvh_device_kernel_ms < 50.0
+    s2 = d2.scene()                                   # lr_scene_create validates that the node array is a tree
+    pd, td = s2.trace_primary()
+    assert np.array_equal(pd, pg) and np.array_equal(td, tg)
+    p2, t2, n2 = s2.trace_rays(org, dirs, normals=True)
+    assert np.array_equal(p2, ph) and np.array_equal(t2, th) and np.array_equal(n2, nh)
+    img_d, _, st_d = s2.render(spp=4, seed=3, splits=1, crop=(x, y, 128, 128))
+    assert st_d["rays"] == st_h["rays"] and np.array_equal(img_d, img_h, equal_nan=True)
+    # and against the oracle directly
+    po, to = o.trace_primary()
+    assert (pd == po).mean() >= 0.9999
+    d2.rebuild_bvh("host")                            # leave the shared fixture as the other tests expect it
+    assert d2.config.bvh_builder == 0 and d2.desc.contents.n_nodes == host_nodes

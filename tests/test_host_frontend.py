@@ -554,3 +554,24 @@ def test_bvh_build_survives_degenerate_meshes(lr, monkeypatch, case):
     assert np.all(seen == 1)
     par = build(8)
     assert np.array_equal(par[0], nodes) and par[1:4] == (n_tri, n_flat, depth) and np.array_equal(par[4], prim)
+
+
+def test_device_bvh_builder_refuses_loudly_without_a_gpu(lr, assets):
+    """LR_BVH_DEVICE is CUDA code with no CPU fallback: without a device the rebuild fails with LR_ERR_NO_DEVICE and the
+    scene keeps its host-built tree; small meshes (< 1024 triangles) always take the host builder."""
+    import torch
+    from lumillyrender_b200.capi import LumillyError
+    d = load_scene(lr, "sample", (64, 64))
+    nodes = d.desc.contents.n_nodes
+    assert d.config.bvh_builder == 0 and nodes > 1000
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(LumillyError) as e:
+        d.rebuild_bvh("device")
+    assert e.value.code == -2 and "no CPU fallback" in e.value.message
+    assert d.desc.contents.n_nodes == nodes and d.config.bvh_builder == 0      # the host-built tree is still there
+    with pytest.raises(LumillyError):
+        d.rebuild_bvh(7)
+    small = load_scene(lr, "new-cbox", (32, 32))
+    small.rebuild_bvh("device")                       # flat-only scene: nothing to build, no device needed
+    assert small.config.bvh_builder == 0

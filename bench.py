@@ -175,16 +175,17 @@ def workload_config(n_gpus, n_prims):
 
 def byte_model(cst, n_flat):
     """Algorithmic bytes per ray from the instrumented kernel's counters: 64 B per BVH node visited, 48 B per
-    triangle tested, 16 B per sphere tested — split into what the TREE costs (nodes + leaf triangles: ray-dependent
-    addresses, served by L2) and what the FLAT LIST costs (every ray tests the same n_flat large triangles in the same
-    order: a warp-uniform broadcast served by L1)."""
+    triangle tested, 32 B per flat-list box gated, 16 B per sphere tested — split into what the TREE costs (nodes + leaf
+    triangles: ray-dependent addresses, served by L2) and what the FLAT LIST costs (every ray gates the same few boxes in the
+    same order and tests the triangles whose box its line crosses: a handful of cache lines that live in L1)."""
     rays = max(cst["rays"], 1)
     nodes, tris, sph = cst["nodes_visited"] / rays, cst["tris_tested"] / rays, cst["spheres_tested"] / rays
-    flat = min(float(n_flat), tris)
+    flat, boxes = cst["flat_tris_tested"] / rays, cst["flat_boxes_tested"] / rays
     tree_b = NODE_BYTES * nodes + TRI_BYTES * (tris - flat)
-    flat_b = TRI_BYTES * flat + SPHERE_BYTES * sph
+    flat_b = TRI_BYTES * flat + 32 * boxes + SPHERE_BYTES * sph
     return {"bytes_per_ray": tree_b + flat_b, "tree_bytes_per_ray": tree_b, "flat_list_bytes_per_ray": flat_b,
-            "nodes_per_ray": nodes, "tree_tris_per_ray": tris - flat, "flat_tris_per_ray": flat, "spheres_per_ray": sph}
+            "nodes_per_ray": nodes, "tree_tris_per_ray": tris - flat, "flat_tris_per_ray": flat, "flat_boxes_per_ray": boxes,
+            "flat_list_size": int(n_flat), "spheres_per_ray": sph}
 
 
 def kernel_name(d):

@@ -165,6 +165,8 @@ typedef struct LrStats {
   uint64_t nonfinite_samples;  /* samples whose estimate was NaN/Inf (kept, as the reference does) */
   uint64_t gate_retraces;      /* rays re-traced strictly because their optimistic nearest BVH hit failed the
                                   reference's leaf-AABB gate (a few per 10^8 rays)                  */
+  uint64_t flat_tris_tested;   /* only if count_traversal: the part of tris_tested that ran on the flat list ...   */
+  uint64_t flat_boxes_tested;  /* ... and the leaf-AABB gate tests that selected those candidates                  */
   float kernel_ms;             /* CUDA-event time of the render kernel(s)        */
   int32_t launches;            /* kernels launched by the call                    */
   int32_t splits;              /* splits actually used                            */

@@ -62,7 +62,8 @@ class LrRenderParams(C.Structure):
 
 class LrStats(C.Structure):
     _fields_ = [("rays", u64), ("samples", u64), ("nodes_visited", u64), ("tris_tested", u64), ("spheres_tested", u64),
-                ("nonfinite_samples", u64), ("gate_retraces", u64), ("kernel_ms", f32), ("launches", i32), ("splits", i32)]
+                ("nonfinite_samples", u64), ("gate_retraces", u64), ("flat_tris_tested", u64), ("flat_boxes_tested", u64),
+                ("kernel_ms", f32), ("launches", i32), ("splits", i32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -210,7 +210,7 @@ static int lr_scene_create_body(const LrSceneDesc* d, LrScene** out) {
           tris[3 * (size_t)i + 2] = mk4(e2[0], e2[1], e2[2], 0.0f);
           // Triangle::aabb (triangle.rs:102-119): min / max of the vertices
           tri_box[2 * (size_t)i + 0] = mk4(std::fmin(std::fmin(t.p0[0], t.p1[0]), t.p2[0]), std::fmin(std::fmin(t.p0[1], t.p1[1]), t.p2[1]),
-                                           std::fmin(std::fmin(t.p0[2], t.p1[2]), t.p2[2]), 0.0f);
+                                           std::fmin(std::fmin(t.p0[2], t.p1[2]), t.p2[2]), 0.0f);   // .w: same box as the predecessor (flat list, below)
           tri_box[2 * (size_t)i + 1] = mk4(std::fmax(std::fmax(t.p0[0], t.p1[0]), t.p2[0]), std::fmax(std::fmax(t.p0[1], t.p1[1]), t.p2[1]),
                                            std::fmax(std::fmax(t.p0[2], t.p1[2]), t.p2[2]), 0.0f);
           // triangle.rs:36  normal = (p1 - p0).cross(p2 - p0).normalize(), in the reference's fp32 operation order
@@ -235,6 +235,12 @@ static int lr_scene_create_body(const LrSceneDesc* d, LrScene** out) {
         pack_tris(0, std::min(d->n_triangles, per));
         if (started < workers) pack_tris(std::min(d->n_triangles, started * per), d->n_triangles);
         for (std::thread& th : pool.v) th.join();
+      }
+      // flat list: a triangle whose box equals its predecessor's (the two halves of a wall quad) shares that gate test
+      for (int i = d->n_triangles - d->n_flat_triangles + 1; i < d->n_triangles; i++) {
+        const float4 *a = tri_box + 2 * (size_t)(i - 1), *b = tri_box + 2 * (size_t)i;
+        if (a[0].x == b[0].x && a[0].y == b[0].y && a[0].z == b[0].z && a[1].x == b[1].x && a[1].y == b[1].y && a[1].z == b[1].z)
+          tri_box[2 * (size_t)i].w = 1.0f;
       }
       for (int i = 0; i < d->n_spheres; i++) {
         const LrSphere& sp = d->spheres[i];
@@ -438,6 +444,7 @@ int lr_stats_fetch(const LrScene* s, void* cuda_stream, LrStats* stats) {
   std::memset(stats, 0, sizeof(*stats));
   stats->rays = c[C_RAYS]; stats->nonfinite_samples = c[C_NONFINITE]; stats->gate_retraces = c[C_RETRACE];
   stats->nodes_visited = c[C_NODES]; stats->tris_tested = c[C_TRIS]; stats->spheres_tested = c[C_SPHERES];
+  stats->flat_tris_tested = c[C_FLAT_TRIS]; stats->flat_boxes_tested = c[C_FLAT_BOXES];
   stats->samples = s->acc_samples; stats->kernel_ms = s->acc_kernel_ms; stats->launches = s->acc_launches; stats->splits = s->last_splits;
   s->acc_samples = 0; s->acc_kernel_ms = 0.0f; s->acc_launches = 0;
   return LR_OK;
@@ -675,6 +682,7 @@ static int lr_render_multi_body(const LrSceneDesc* desc, const LrRenderParams* p
       if ((rc = lr_stats_fetch(scenes[i], nullptr, &st)) != LR_OK) break;
       total.rays += st.rays; total.samples += st.samples; total.nodes_visited += st.nodes_visited; total.tris_tested += st.tris_tested;
       total.spheres_tested += st.spheres_tested; total.nonfinite_samples += st.nonfinite_samples; total.gate_retraces += st.gate_retraces;
+      total.flat_tris_tested += st.flat_tris_tested; total.flat_boxes_tested += st.flat_boxes_tested;
       total.kernel_ms = std::max(total.kernel_ms, st.kernel_ms);
       total.launches += st.launches;
       total.splits = std::max(total.splits, st.splits);

@@ -158,7 +158,23 @@ LR_DEV float sphere_hit(F3 c, float r, F3 o, F3 d) {
   return t;
 }
 
-struct TraceCounters { unsigned int nodes, tris, spheres; };
+// The same test without the early exits (select form): mn only rises and mx only falls from axis to axis (a NaN bound fails
+// its comparison and changes nothing, as in the reference), so `mn > mx` after some axis implies `mn > mx` at the end.
+LR_DEV bool ref_slab_pass_select(F3 lo, F3 hi, F3 o, F3 inv) {
+  float mn = -kINF, mx = kINF;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const float t1 = (comp(lo, i) - comp(o, i)) * comp(inv, i);
+    const float t2 = (comp(hi, i) - comp(o, i)) * comp(inv, i);
+    const bool sw = t1 > t2;
+    const float t_min = sw ? t2 : t1, t_max = sw ? t1 : t2;
+    mn = mn < t_min ? t_min : mn;
+    mx = mx > t_max ? t_max : mx;
+  }
+  return !(mn > mx);
+}
+
+struct TraceCounters { unsigned int nodes, tris, spheres, flat_tris, flat_boxes; };
 
 LR_DEV float4 ldg4(const float4* p) { return __ldg(p); }
 
@@ -168,19 +184,20 @@ LR_DEV bool tri_gate(const DevScene& sc, F3 o, F3 inv, int id) {
   const float4* bp = sc.tri_box + 2 * (size_t)id;
   return ref_slab_pass(f3(ldg4(bp + 0)), f3(ldg4(bp + 1)), o, inv);
 }
-// flat triangle list with the gate on every candidate (the rare fallback of flat_hits), out of line
-static __device__ __noinline__ void flat_tris_strict(const DevScene& sc, F3 o, F3 d, F3 inv, float* best_t, int* best) {
-  for (int i = sc.n_bvh_tris; i < sc.n_tris; i++) {
-    const float4* tp = sc.tris + 3 * (size_t)i;
-    const float t = triangle_mt(f3(ldg4(tp + 0)), f3(ldg4(tp + 1)), f3(ldg4(tp + 2)), o, d);
-    if (t >= 0.0f && t < *best_t && tri_gate(sc, o, inv, i)) { *best_t = t; *best = i; }
-  }
-}
-
 // Candidates every ray tests in a fixed order, with the reference's exact arithmetic and its leaf-AABB gate:
 // the spheres (no culling at all: the r = 1e5 ground sphere of scenes/primitive.toml has a t error far larger
 // than any box slack), then the flat list of large triangles tris[n_bvh_tris, n_tris) (bvh_build.cpp).
 // id: -1 miss, >= 0 triangle index, <= -2 sphere index = -2 - id.
+//
+// Flat triangles go through the reference's own two steps in the reference's order: Leaf::may_intersect — the line-slab
+// test on the triangle's own box (bvh.rs:21-25, aabb.rs:75-92) — selects the candidates, then the primitive test runs on
+// those alone, in index order with a strict `<` (the first minimum wins, bvh.rs:136-140).  The gate is what makes a
+// candidate valid, so testing it first is exact by construction; it is also cheap and selective: the line of a ray inside
+// a room crosses the (flat) boxes of two walls, so a lane runs Moller-Trumbore on ~4-6 of the ~12-16 flat triangles.
+//   * lanes hold DIFFERENT candidates in the second loop (a bit mask per lane, lowest bit first): the loop is as long as the
+//     lane with the most candidates needs, not as long as the list;
+//   * consecutive flat triangles with the same box (the two halves of a wall quad) share one gate test: tri_box[2i].w is 1
+//     where triangle i's box equals its predecessor's (set at upload, api.cpp).
 template <bool COUNT>
 LR_DEV void flat_hits(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, int& best, TraceCounters& tc) {
   for (int i = 0; i < sc.n_spheres; i++) {
@@ -193,23 +210,28 @@ LR_DEV void flat_hits(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, int
       if (ref_slab_pass(c - r, c + r, o, inv)) { best_t = t; best = -2 - i; }
     }
   }
-  // flat triangles: optimistic pass (accept the nearest candidate ungated), then ONE gate test on the winner; if the
-  // gate rejects it (fp corner cases, hits beyond t = 1e5) the list is re-run with the gate on every candidate.  If the
-  // winner passes it is the gated nearest hit (the minimum over a superset that lies in the subset, same order).
-  const float t_sph = best_t;
-  const int b_sph = best;
+  const int n_flat = sc.n_tris - sc.n_bvh_tris;                    // <= 24 (bvh_build.cpp: kFlatMax)
+  unsigned cand = 0u;
+  bool pass = false;
 #pragma unroll 1
-  for (int i = sc.n_bvh_tris; i < sc.n_tris; i++) {
+  for (int k = 0; k < n_flat; k++) {
+    const float4* bp = sc.tri_box + 2 * (size_t)(sc.n_bvh_tris + k);
+    const float4 lo = ldg4(bp + 0), hi = ldg4(bp + 1);
+    if (lo.w == 0.0f) {                                            // warp-uniform: a new box
+      pass = ref_slab_pass_select(f3(lo), f3(hi), o, inv);
+      if (COUNT) tc.flat_boxes++;
+    }
+    if (pass) cand |= 1u << k;
+  }
+#pragma unroll 1
+  while (cand != 0u) {
+    const int i = sc.n_bvh_tris + __ffs(cand) - 1;
+    cand &= cand - 1u;
     const float4* tp = sc.tris + 3 * (size_t)i;
     const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
-    if (COUNT) tc.tris++;
+    if (COUNT) { tc.tris++; tc.flat_tris++; }
     const float t = triangle_mt(f3(v0), f3(v1), f3(v2), o, d);
     if (t >= 0.0f && t < best_t) { best_t = t; best = i; }
-  }
-  if (best != b_sph && !tri_gate(sc, o, inv, best)) {
-    best_t = t_sph;
-    best = b_sph;
-    flat_tris_strict(sc, o, d, inv, &best_t, &best);
   }
 }
 

@@ -5,7 +5,8 @@
 //   nodes    : 4 x float4 per BVH node   (64 B)   — two child boxes + child codes
 //   tris     : 3 x float4 per triangle   (48 B)   — p0|prim_id, e1 = p1-p0|material, e2 = p2-p0|0   (BVH leaf order,
 //                                                   then the flat list of large triangles every ray tests)
-//   tri_box  : 2 x float4 per triangle   (32 B)   — box of the vertices (cold: read once per ray, for the gate)
+//   tri_box  : 2 x float4 per triangle   (32 B)   — box of the vertices (lo | same-box-as-predecessor flag, hi | 0): the reference's
+//                                                   leaf-AABB gate — once per ray for the nearest tree hit, once per flat box
 //   tri_n    : 1 x float4 per triangle   (16 B)   — unit geometric normal | 0 (read once per path vertex)
 //   spheres  : 1 x float4 per sphere     (16 B)   — centre|radius     (+ int2 material/prim_id)
 //   mats     : 3 x float4 per material   (48 B)   — colour|type, emission|param0, param1|weight|emissive|0
@@ -56,6 +57,6 @@ struct DevParams {
 };
 
 // device counter block (unsigned long long each)
-enum CounterSlot { C_RAYS = 0, C_NONFINITE = 1, C_NODES = 2, C_TRIS = 3, C_SPHERES = 4, C_RETRACE = 5, C_NEXT_UNIT = 7, C_COUNT = 8 };
+enum CounterSlot { C_RAYS = 0, C_NONFINITE = 1, C_NODES = 2, C_TRIS = 3, C_SPHERES = 4, C_RETRACE = 5, C_FLAT_TRIS = 6, C_NEXT_UNIT = 7, C_FLAT_BOXES = 8, C_COUNT = 9 };
 
 }  // namespace lr

@@ -107,7 +107,7 @@ render_persistent_kernel(const __grid_constant__ DevScene sc, const __grid_const
   bool alive = true;
   unsigned int n_nonfinite = 0, n_retrace = 0, n_rays = 0;
   TraceCounters tc;
-  tc.nodes = tc.tris = tc.spheres = 0;
+  tc.nodes = tc.tris = tc.spheres = tc.flat_tris = tc.flat_boxes = 0;
 
   while (true) {
     // ================================================================ phase A
@@ -115,7 +115,18 @@ render_persistent_kernel(const __grid_constant__ DevScene sc, const __grid_const
       const bool ready = alive && !(pend0 || pend1);
       if (!__any_sync(kFull, ready)) break;
       // one path vertex for the lanes that hold a resolved hit: shade, regenerate, flat list + tree bounds for the new ray(s)
+      // (a lane owns its path: the whole state stays in the lane's variables, the hooks are empty)
+#define PV_LOAD_SHADOW()
+#define PV_STORE_SHADOW()
+#define PV_STORE_QBRDF()
+#define PV_LOAD_FILM()
+#define PV_STORE_FILM()
 #include "path_vertex.inc"
+#undef PV_LOAD_SHADOW
+#undef PV_STORE_SHADOW
+#undef PV_STORE_QBRDF
+#undef PV_LOAD_FILM
+#undef PV_STORE_FILM
       if (__popc(__ballot_sync(kFull, pend0 || pend1)) >= p.defer_thresh) break;
     }
 
@@ -147,7 +158,10 @@ render_persistent_kernel(const __grid_constant__ DevScene sc, const __grid_const
   n_rays = warp_sum_u(n_rays);
   n_nonfinite = warp_sum_u(n_nonfinite);
   n_retrace = warp_sum_u(n_retrace);
-  if (COUNT) { tc.nodes = warp_sum_u(tc.nodes); tc.tris = warp_sum_u(tc.tris); tc.spheres = warp_sum_u(tc.spheres); }
+  if (COUNT) {
+    tc.nodes = warp_sum_u(tc.nodes); tc.tris = warp_sum_u(tc.tris); tc.spheres = warp_sum_u(tc.spheres);
+    tc.flat_tris = warp_sum_u(tc.flat_tris); tc.flat_boxes = warp_sum_u(tc.flat_boxes);
+  }
   if (lane == 0) {
     if (n_rays) atomicAdd(counters + C_RAYS, (unsigned long long)n_rays);
     if (n_nonfinite) atomicAdd(counters + C_NONFINITE, (unsigned long long)n_nonfinite);
@@ -156,6 +170,8 @@ render_persistent_kernel(const __grid_constant__ DevScene sc, const __grid_const
       atomicAdd(counters + C_NODES, (unsigned long long)tc.nodes);
       atomicAdd(counters + C_TRIS, (unsigned long long)tc.tris);
       atomicAdd(counters + C_SPHERES, (unsigned long long)tc.spheres);
+      atomicAdd(counters + C_FLAT_TRIS, (unsigned long long)tc.flat_tris);
+      atomicAdd(counters + C_FLAT_BOXES, (unsigned long long)tc.flat_boxes);
     }
   }
 }

@@ -25,10 +25,15 @@ namespace lr {
 
 // Tunables, each settled by A/B runs on one box (profiles/r01_e_ab_s39.txt, s43-s49): paths per warp (64, 96 or 128: no gain
 // beyond 64), pending rays that start a BVH phase (24: slower, 48: same), resident CTAs per SM asked of the register
-// allocator (pt: 4..8 within 3 %, 6 = 80 registers; pt-direct: 4 = 127 registers without spills, its 42-word slots
-// allow 5 at most).
+// allocator (pt: 4..8 within 3 %, 6 = 80 registers; pt-direct: 6 since the vertex fetches its shadow and film records where
+// it uses them — with the whole 42-word slot live across the vertex it needed 125 registers).
 #ifndef LR_POOL_SLOTS
 #define LR_POOL_SLOTS 64
+#endif
+// pt-direct slots hold the shadow-ray record too (42 words against 26): 48 of them per warp keep a CTA at 32 KB, so that
+// six CTAs (24 warps) fit an SM's 227 KB like the pt build's; 64 leave room for five
+#ifndef LR_POOL_SLOTS_PTD
+#define LR_POOL_SLOTS_PTD 48
 #endif
 #ifndef LR_POOL_BSTART
 #define LR_POOL_BSTART 32
@@ -37,7 +42,7 @@ namespace lr {
 #define LR_PMB_PT_TREE 6
 #endif
 #ifndef LR_PMB_PTD_TREE
-#define LR_PMB_PTD_TREE 4
+#define LR_PMB_PTD_TREE 6
 #endif
 
 namespace pl {
@@ -50,16 +55,20 @@ enum {
   W_PTD_COUNT
 };
 
-constexpr int kSlots = LR_POOL_SLOTS;
-static_assert(kSlots % 32 == 0 && kSlots >= 64 && kSlots <= 128, "a warp's pool holds 64, 96 or 128 paths");
-constexpr int kWords = kSlots / 32;                     // mask words per kind of work
+// paths per warp: more than the 32 lanes (that is the point), a multiple of 16; the last mask word may be partly used
+template <int INTEGRATOR>
+__host__ __device__ constexpr int slots() { return INTEGRATOR == LR_INTEGRATOR_PT_DIRECT ? LR_POOL_SLOTS_PTD : LR_POOL_SLOTS; }
+static_assert(LR_POOL_SLOTS % 16 == 0 && LR_POOL_SLOTS >= 48 && LR_POOL_SLOTS <= 128, "a warp's pool holds 48 .. 128 paths");
+static_assert(LR_POOL_SLOTS_PTD % 16 == 0 && LR_POOL_SLOTS_PTD >= 48 && LR_POOL_SLOTS_PTD <= 128, "a warp's pool holds 48 .. 128 paths");
+template <int INTEGRATOR>
+__host__ __device__ constexpr int mask_words() { return (slots<INTEGRATOR>() + 31) / 32; }     // mask words per kind of work
 
 template <int INTEGRATOR>
 __host__ __device__ constexpr int words_per_slot(bool want_sumsq) {
   return (INTEGRATOR == LR_INTEGRATOR_PT_DIRECT ? (int)W_PTD_COUNT : (int)W_PT_COUNT) + (want_sumsq ? 3 : 0);
 }
 template <int INTEGRATOR>
-__host__ __device__ constexpr int warp_words(bool want_sumsq) { return words_per_slot<INTEGRATOR>(want_sumsq) * kSlots + 32; }
+__host__ __device__ constexpr int warp_words(bool want_sumsq) { return words_per_slot<INTEGRATOR>(want_sumsq) * slots<INTEGRATOR>() + 32; }
 
 // Takes the first `quota` set bits of the concatenation words[rot] | words[rot + 1] | ... (cyclic): their codes
 // word * 32 + bit go to list[0, n) in that order, the bits are cleared in `words`.  Returns n (warp-uniform).  Lane j
@@ -105,7 +114,8 @@ render_pool_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ 
   using namespace pk;
   using namespace pl;
   constexpr int NR = INTEGRATOR == LR_INTEGRATOR_PT_DIRECT ? 2 : 1;     // rays a vertex can issue: extension (+ shadow)
-  constexpr int NS = kSlots;
+  constexpr int NS = slots<INTEGRATOR>();
+  constexpr int kWords = mask_words<INTEGRATOR>();
   extern __shared__ float pool_smem[];
   const int lane = (int)(threadIdx.x & 31);
   const unsigned int n_units = (unsigned int)p.tiles_x * p.tiles_y * 32u * (unsigned int)p.splits;
@@ -126,10 +136,10 @@ render_pool_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ 
 #pragma unroll
   for (int i = 0; i < NR * kWords; i++) pend[i] = 0u;
 #pragma unroll
-  for (int i = 0; i < kWords; i++) dead[i] = 0u;
+  for (int i = 0; i < kWords; i++) dead[i] = (i + 1) * 32 <= NS ? 0u : ~0u << (NS - i * 32);   // slots beyond NS do not exist
   unsigned int n_nonfinite = 0, n_retrace = 0, n_rays = 0;
   TraceCounters tc;
-  tc.nodes = tc.tris = tc.spheres = 0;
+  tc.nodes = tc.tris = tc.spheres = tc.flat_tris = tc.flat_boxes = 0;
   int rot_a = 0, rot_b = 0;
 
   while (true) {
@@ -165,49 +175,67 @@ render_pool_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ 
       F3 q_T = f3(0, 0, 0), q_brdf = f3(0, 0, 0);
       float q_prr = 1.0f, q_point_cos = 0.0f, q_dist = 0.0f, q_sqr = 1.0f, q_pdf = 1.0f;
       int flags = 0;
+      // the state every vertex needs: ray, hit, throughput, radiance, RNG, flags.  The shadow-ray record (16 words) and the
+      // film record (pixel sums, unit, camera weights: 12-15 words) are fetched by the vertex code where it needs them
+      // (PV_LOAD_* hooks below) and are not live across the surface / light-sample / BSDF code in between
       if (ready) {
         o = f3(SLF(W_OX), SLF(W_OY), SLF(W_OZ));
         d0 = f3(SLF(W_DX), SLF(W_DY), SLF(W_DZ));
         t0 = SLF(W_T0); id0 = SLI(W_ID0);
         T = f3(SLF(W_TX), SLF(W_TY), SLF(W_TZ));
         L = f3(SLF(W_LX), SLF(W_LY), SLF(W_LZ));
-        sum = f3(SLF(W_SX), SLF(W_SY), SLF(W_SZ));
-        cam_g = SLF(W_CAMG); cam_w = SLF(W_CAMW);
-        un = make_int4(SLI(W_UNX), SLI(W_UNY), SLI(W_UNZ), SLI(W_UNW));
         rng.state = (unsigned long long)(unsigned int)SLI(W_RNGLO) | ((unsigned long long)(unsigned int)SLI(W_RNGHI) << 32);
         flags = SLI(W_FLAGS);
-        if (NR == 2) {
-          d1 = f3(SLF(W_D1X), SLF(W_D1Y), SLF(W_D1Z));
-          t1 = SLF(W_T1); id1 = SLI(W_ID1);
-          q_T = f3(SLF(W_QTX), SLF(W_QTY), SLF(W_QTZ));
-          q_brdf = f3(SLF(W_QBX), SLF(W_QBY), SLF(W_QBZ));
-          q_prr = SLF(W_QPRR); q_point_cos = SLF(W_QPC); q_dist = SLF(W_QDIST); q_sqr = SLF(W_QSQR); q_pdf = SLF(W_QPDF);
-        }
-        if (want_sumsq) sumsq = f3(SLF(W_SQ), SLF(W_SQ + 1), SLF(W_SQ + 2));
       }
+#define PV_LOAD_SHADOW()                                                                                                  \
+  do {                                                                                                                    \
+    d1 = f3(SLF(W_D1X), SLF(W_D1Y), SLF(W_D1Z));                                                                          \
+    t1 = SLF(W_T1); id1 = SLI(W_ID1);                                                                                     \
+    q_T = f3(SLF(W_QTX), SLF(W_QTY), SLF(W_QTZ));                                                                         \
+    q_brdf = f3(SLF(W_QBX), SLF(W_QBY), SLF(W_QBZ));                                                                      \
+    q_prr = SLF(W_QPRR); q_point_cos = SLF(W_QPC); q_dist = SLF(W_QDIST); q_sqr = SLF(W_QSQR); q_pdf = SLF(W_QPDF);       \
+  } while (0)
+#define PV_STORE_SHADOW()                                                                                                 \
+  do {                                                                                                                    \
+    SLF(W_QTX) = q_T.x; SLF(W_QTY) = q_T.y; SLF(W_QTZ) = q_T.z;                                                           \
+    SLF(W_QPRR) = q_prr; SLF(W_QPC) = q_point_cos; SLF(W_QDIST) = q_dist; SLF(W_QSQR) = q_sqr; SLF(W_QPDF) = q_pdf;       \
+  } while (0)
+#define PV_STORE_QBRDF() do { SLF(W_QBX) = q_brdf.x; SLF(W_QBY) = q_brdf.y; SLF(W_QBZ) = q_brdf.z; } while (0)
+#define PV_LOAD_FILM()                                                                                                    \
+  do {                                                                                                                    \
+    sum = f3(SLF(W_SX), SLF(W_SY), SLF(W_SZ));                                                                            \
+    cam_g = SLF(W_CAMG); cam_w = SLF(W_CAMW);                                                                             \
+    un = make_int4(SLI(W_UNX), SLI(W_UNY), SLI(W_UNZ), SLI(W_UNW));                                                       \
+    if (want_sumsq) sumsq = f3(SLF(W_SQ), SLF(W_SQ + 1), SLF(W_SQ + 2));                                                  \
+  } while (0)
+#define PV_STORE_FILM()                                                                                                   \
+  do {                                                                                                                    \
+    SLF(W_SX) = sum.x; SLF(W_SY) = sum.y; SLF(W_SZ) = sum.z;                                                              \
+    SLF(W_CAMG) = cam_g; SLF(W_CAMW) = cam_w;                                                                             \
+    SLI(W_UNX) = un.x; SLI(W_UNY) = un.y; SLI(W_UNZ) = un.z; SLI(W_UNW) = un.w;                                           \
+    if (want_sumsq) { SLF(W_SQ) = sumsq.x; SLF(W_SQ + 1) = sumsq.y; SLF(W_SQ + 2) = sumsq.z; }                            \
+  } while (0)
 
       // the vertex itself: the code of persistent.cuh's phase A, on the variables loaded above
 #include "path_vertex.inc"
 
+#undef PV_LOAD_SHADOW
+#undef PV_STORE_SHADOW
+#undef PV_STORE_QBRDF
+#undef PV_LOAD_FILM
+#undef PV_STORE_FILM
       if (go) {
         SLF(W_OX) = o.x; SLF(W_OY) = o.y; SLF(W_OZ) = o.z;
         SLF(W_DX) = d0.x; SLF(W_DY) = d0.y; SLF(W_DZ) = d0.z;
         SLF(W_T0) = t0; SLI(W_ID0) = id0;
         SLF(W_TX) = T.x; SLF(W_TY) = T.y; SLF(W_TZ) = T.z;
         SLF(W_LX) = L.x; SLF(W_LY) = L.y; SLF(W_LZ) = L.z;
-        SLF(W_SX) = sum.x; SLF(W_SY) = sum.y; SLF(W_SZ) = sum.z;
-        SLF(W_CAMG) = cam_g; SLF(W_CAMW) = cam_w;
-        SLI(W_UNX) = un.x; SLI(W_UNY) = un.y; SLI(W_UNZ) = un.z; SLI(W_UNW) = un.w;
         SLI(W_RNGLO) = (int)(unsigned int)rng.state; SLI(W_RNGHI) = (int)(unsigned int)(rng.state >> 32);
         SLI(W_FLAGS) = flags;
-        if (NR == 2) {
+        if (NR == 2 && (flags & F_HAS_SHADOW)) {               // the shadow ray made by this vertex (its record went to the slot where it was computed)
           SLF(W_D1X) = d1.x; SLF(W_D1Y) = d1.y; SLF(W_D1Z) = d1.z;
           SLF(W_T1) = t1; SLI(W_ID1) = id1;
-          SLF(W_QTX) = q_T.x; SLF(W_QTY) = q_T.y; SLF(W_QTZ) = q_T.z;
-          SLF(W_QBX) = q_brdf.x; SLF(W_QBY) = q_brdf.y; SLF(W_QBZ) = q_brdf.z;
-          SLF(W_QPRR) = q_prr; SLF(W_QPC) = q_point_cos; SLF(W_QDIST) = q_dist; SLF(W_QSQR) = q_sqr; SLF(W_QPDF) = q_pdf;
         }
-        if (want_sumsq) { SLF(W_SQ) = sumsq.x; SLF(W_SQ + 1) = sumsq.y; SLF(W_SQ + 2) = sumsq.z; }
       }
       // new slot states
       const unsigned bit = 1u << (s & 31);
@@ -227,9 +255,9 @@ render_pool_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ 
       const int n_sel = select_take<NR * kWords>(list, lane, pend, 32, rot_b);
       rot_b = rot_b + 1 == NR * kWords ? 0 : rot_b + 1;
       if (lane < n_sel) {
-        const int item = list[lane];
-        const int s = item % NS;
-        const bool shadow = NR == 2 && item >= NS;
+        const int item = list[lane];                          // mask word * 32 + bit; the shadow rays' words follow the kWords extension words
+        const int s = item % (32 * kWords);
+        const bool shadow = NR == 2 && item >= 32 * kWords;
         const F3 o = f3(SLF(W_OX), SLF(W_OY), SLF(W_OZ));
         const F3 d = shadow ? f3(SLF(W_D1X), SLF(W_D1Y), SLF(W_D1Z)) : f3(SLF(W_DX), SLF(W_DY), SLF(W_DZ));
         const F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
@@ -252,7 +280,10 @@ render_pool_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ 
   n_rays = warp_sum_u(n_rays);
   n_nonfinite = warp_sum_u(n_nonfinite);
   n_retrace = warp_sum_u(n_retrace);
-  if (COUNT) { tc.nodes = warp_sum_u(tc.nodes); tc.tris = warp_sum_u(tc.tris); tc.spheres = warp_sum_u(tc.spheres); }
+  if (COUNT) {
+    tc.nodes = warp_sum_u(tc.nodes); tc.tris = warp_sum_u(tc.tris); tc.spheres = warp_sum_u(tc.spheres);
+    tc.flat_tris = warp_sum_u(tc.flat_tris); tc.flat_boxes = warp_sum_u(tc.flat_boxes);
+  }
   if (lane == 0) {
     if (n_rays) atomicAdd(counters + C_RAYS, (unsigned long long)n_rays);
     if (n_nonfinite) atomicAdd(counters + C_NONFINITE, (unsigned long long)n_nonfinite);
@@ -261,6 +292,8 @@ render_pool_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ 
       atomicAdd(counters + C_NODES, (unsigned long long)tc.nodes);
       atomicAdd(counters + C_TRIS, (unsigned long long)tc.tris);
       atomicAdd(counters + C_SPHERES, (unsigned long long)tc.spheres);
+      atomicAdd(counters + C_FLAT_TRIS, (unsigned long long)tc.flat_tris);
+      atomicAdd(counters + C_FLAT_BOXES, (unsigned long long)tc.flat_boxes);
     }
   }
 }
@@ -277,7 +310,7 @@ cudaError_t launch_pool_one(const DevScene& sc, const DevParams& p, float* out_s
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kBlockThreads, smem) != cudaSuccess || nb <= 0) nb = 2;
   // a warp serves kSlots units at a time
   const long long units = (long long)p.tiles_x * p.tiles_y * 32 * p.splits;
-  const long long per_block = (long long)(kBlockThreads / 32) * pl::kSlots;
+  const long long per_block = (long long)(kBlockThreads / 32) * pl::slots<INTEGRATOR>();
   const long long want = (units + per_block - 1) / per_block;
   const unsigned int blocks = (unsigned int)std::max<long long>(1, std::min<long long>(want, (long long)nb * sm_count));
   kernel<<<blocks, kBlockThreads, smem, stream>>>(sc, p, out_sum, out_sumsq, counters, next_unit);

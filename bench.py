@@ -192,7 +192,8 @@ def kernel_name(d):
     desc = d.desc.contents
     integ = "pt" if d.config.integrator == 0 else "pt-direct"
     tree = desc.n_nodes > 0
-    return "%s<%s, %s>" % ("render_pool_kernel" if tree else "render_persistent_kernel", integ, "tree" if tree else "flat")
+    pool = tree and d.config.integrator == 0            # persistent_inst.cu: LR_USE_POOL
+    return "%s<%s, %s>" % ("render_pool_kernel" if pool else "render_persistent_kernel", integ, "tree" if tree else "flat")
 
 
 def run_configs(lr, torch, l2_peak, hbm_peak):

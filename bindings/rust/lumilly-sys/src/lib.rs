@@ -28,14 +28,22 @@ use std::os::raw::{c_char, c_int, c_void};
 }
 #[repr(C)] #[derive(Clone, Copy, Default)] pub struct LrStats {
     pub rays: u64, pub samples: u64, pub nodes_visited: u64, pub tris_tested: u64, pub spheres_tested: u64, pub nonfinite_samples: u64,
-    pub gate_retraces: u64, pub kernel_ms: f32, pub launches: i32, pub splits: i32,
+    pub gate_retraces: u64, pub flat_tris_tested: u64, pub flat_boxes_tested: u64, pub kernel_ms: f32, pub launches: i32, pub splits: i32,
 }
 #[repr(C)] #[derive(Clone, Copy, Default)] pub struct LrSceneConfig {
     pub samples: i32, pub depth: i32, pub depth_limit: i32, pub no_direct_emitter: i32, pub threads: i32, pub integrator: i32,
     pub width: i32, pub height: i32, pub output: i32, pub gamma: f32, pub n_prims: i32, pub n_emitters: i32, pub bvh_build_seconds: f32,
+    pub bvh_builder: i32, pub bvh_device_kernel_ms: f32,
 }
 pub enum LrScene {}
 pub enum LrHostScene {}
+pub enum LrFilm {}
+pub const LR_AOV_NORMAL: i32 = 0;
+pub const LR_AOV_DEPTH: i32 = 1;
+pub const LR_BVH_HOST: i32 = 0;
+pub const LR_BVH_DEVICE: i32 = 1;
+pub const LR_QUERY_STRICT: i32 = 0;
+pub const LR_QUERY_RENDER: i32 = 1;
 
 extern "C" {
     pub fn lr_abi_version() -> c_int;
@@ -52,7 +60,22 @@ extern "C" {
     /// one peer-reading reduce kernel on devices[0])
     pub fn lr_render_multi(desc: *const LrSceneDesc, params: *const LrRenderParams, n_devices: i32, devices: *const i32,
                            out_rgb: *mut f32, out_sumsq: *mut f32, stats: *mut LrStats) -> c_int;
+    /// Scene::normal / Scene::depth (scene.rs:48-62) of the camera rays of the sample range, averaged per pixel
+    pub fn lr_render_aov(scene: *const LrScene, params: *const LrRenderParams, kind: i32, out: *mut f32) -> c_int;
+    /// progressive / resumable rendering (the hook main.rs:81-91 abandoned): per-pixel sums kept on the device
+    pub fn lr_film_create(scene: *const LrScene, params: *const LrRenderParams, want_sumsq: i32, out: *mut *mut LrFilm) -> c_int;
+    pub fn lr_film_render(film: *mut LrFilm, spp_count: i32, stats: *mut LrStats) -> c_int;
+    pub fn lr_film_info(film: *const LrFilm, spp_done: *mut i32, crop_w: *mut i32, crop_h: *mut i32, has_sumsq: *mut i32) -> c_int;
+    pub fn lr_film_read(film: *const LrFilm, out_rgb: *mut f32, out_sumsq: *mut f32) -> c_int;
+    pub fn lr_film_save(film: *const LrFilm, path: *const c_char) -> c_int;
+    pub fn lr_film_load(scene: *const LrScene, path: *const c_char, out: *mut *mut LrFilm) -> c_int;
+    pub fn lr_film_destroy(film: *mut LrFilm);
     pub fn lr_trace_primary(scene: *const LrScene, u: f32, v: f32, ua: f32, va: f32, prim: *mut i32, t: *mut f32) -> c_int;
+    pub fn lr_trace_rays(scene: *const LrScene, n: i64, origins: *const f32, directions: *const f32, prim: *mut i32, t: *mut f32, normal: *mut f32) -> c_int;
+    pub fn lr_trace_rays_query(scene: *const LrScene, n: i64, origins: *const f32, directions: *const f32, query: i32, prim: *mut i32, t: *mut f32,
+                               normal: *mut f32) -> c_int;
+    /// BVH::new (bvh.rs:57-127) again, by the host's binned-SAH builder or by the device's radix-tree builder
+    pub fn lr_host_scene_rebuild_bvh(hs: *mut LrHostScene, builder: i32) -> c_int;
     pub fn lr_host_scene_load(toml_path: *const c_char, asset_root: *const c_char, w: i32, h: i32, out: *mut *mut LrHostScene) -> c_int;
     pub fn lr_host_scene_from_arrays(materials: *const LrMaterial, n_materials: i32, triangles: *const LrTriangle, n_triangles: i32,
                                      spheres: *const LrSphere, n_spheres: i32, camera: *const LrCamera, sky: *const LrSky,

@@ -257,6 +257,14 @@ int lr_trace_primary(const LrScene* scene, float u, float v, float ua, float va,
 int lr_trace_rays(const LrScene* scene, int64_t n, const float* origins, const float* directions,
                   int32_t* prim, float* t, float* normal /* nullable, n*3 */);
 
+/* the same with the kind of query stated: LR_QUERY_STRICT — the reference's leaf-AABB gate on every candidate (what
+ * lr_trace_rays and lr_trace_primary run); LR_QUERY_RENDER — the query exactly as the render kernels run it (flat list,
+ * tree-bounds test, optimistic traversal, the nearest tree hit gated once, strict re-trace if the gate rejects it).  Both
+ * must answer alike; the second exists so that a replay divergence can be pinned on a ray.                         */
+typedef enum LrQueryKind { LR_QUERY_STRICT = 0, LR_QUERY_RENDER = 1 } LrQueryKind;
+int lr_trace_rays_query(const LrScene* scene, int64_t n, const float* origins, const float* directions, int32_t query,
+                        int32_t* prim, float* t, float* normal /* nullable, n*3 */);
+
 /* ---- measurement helpers ---- */
 int lr_measure_l2_read_gbs(uint64_t working_set_bytes, int iters, float* gbs);
 int lr_measure_hbm_read_gbs(uint64_t bytes, int iters, float* gbs);

@@ -111,6 +111,7 @@ SIGNATURES = {
     "lr_film_destroy": (None, [_VP]),
     "lr_trace_primary": (C.c_int, [_VP, f32, f32, f32, f32, _PI, _PF]),
     "lr_trace_rays": (C.c_int, [_VP, i64, _PF, _PF, _PI, _PF, _PF]),
+    "lr_trace_rays_query": (C.c_int, [_VP, i64, _PF, _PF, i32, _PI, _PF, _PF]),
     "lr_measure_l2_read_gbs": (C.c_int, [u64, C.c_int, _PF]),
     "lr_measure_hbm_read_gbs": (C.c_int, [u64, C.c_int, _PF]),
     "lr_host_scene_load": (C.c_int, [C.c_char_p, C.c_char_p, i32, i32, C.POINTER(_VP)]),

@@ -728,7 +728,13 @@ int lr_trace_primary(const LrScene* s, float u, float v, float ua, float va, int
 }
 
 int lr_trace_rays(const LrScene* s, int64_t n, const float* origins, const float* directions, int32_t* prim, float* t, float* normal) {
+  return lr_trace_rays_query(s, n, origins, directions, LR_QUERY_STRICT, prim, t, normal);
+}
+
+int lr_trace_rays_query(const LrScene* s, int64_t n, const float* origins, const float* directions, int32_t query, int32_t* prim, float* t,
+                        float* normal) {
   if (!s || !origins || !directions || !prim || !t || n < 0) return fail(LR_ERR_INVALID, "bad argument");
+  if (query != LR_QUERY_STRICT && query != LR_QUERY_RENDER) return fail(LR_ERR_INVALID, "unknown query kind");
   if (n == 0) return LR_OK;
   if (int rc = ensure_device()) return rc;
   float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr, *d_n = nullptr; int* d_p = nullptr;
@@ -739,7 +745,7 @@ int lr_trace_rays(const LrScene* s, int64_t n, const float* origins, const float
   if (e == cudaSuccess && normal) e = cudaMalloc((void**)&d_n, n * 3 * sizeof(float));
   if (e == cudaSuccess) e = cudaMemcpy(d_o, origins, n * 3 * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(d_d, directions, n * 3 * sizeof(float), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = launch_rays(s->dev, n, d_o, d_d, d_p, d_t, d_n, 0);
+  if (e == cudaSuccess) e = launch_rays(s->dev, n, d_o, d_d, d_p, d_t, d_n, query == LR_QUERY_RENDER, 0);
   if (e == cudaSuccess) e = cudaMemcpy(prim, d_p, n * sizeof(int), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess) e = cudaMemcpy(t, d_t, n * sizeof(float), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && normal) e = cudaMemcpy(normal, d_n, n * 3 * sizeof(float), cudaMemcpyDeviceToHost);

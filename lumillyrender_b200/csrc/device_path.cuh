@@ -198,6 +198,13 @@ LR_DEV bool tri_gate(const DevScene& sc, F3 o, F3 inv, int id) {
 //     lane with the most candidates needs, not as long as the list;
 //   * consecutive flat triangles with the same box (the two halves of a wall quad) share one gate test: tri_box[2i].w is 1
 //     where triangle i's box equals its predecessor's (set at upload, api.cpp).
+LR_DEV constexpr bool cand_loop_enabled() {
+#ifdef LR_FLAT_ALL
+  return false;
+#else
+  return true;
+#endif
+}
 template <bool COUNT>
 LR_DEV void flat_hits(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, int& best, TraceCounters& tc) {
   for (int i = 0; i < sc.n_spheres; i++) {
@@ -213,8 +220,22 @@ LR_DEV void flat_hits(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, int
   const int n_flat = sc.n_tris - sc.n_bvh_tris;                    // <= 24 (bvh_build.cpp: kFlatMax)
   unsigned cand = 0u;
   bool pass = false;
+#ifdef LR_FLAT_ALL
+  // A/B build (tools/ab.py): the primitive test on every flat triangle, the gate on those that would become the nearest hit
+  cand = n_flat >= 32 ? ~0u : (1u << n_flat) - 1u;
 #pragma unroll 1
-  for (int k = 0; k < n_flat; k++) {
+  while (cand != 0u) {
+    const int i = sc.n_bvh_tris + __ffs(cand) - 1;
+    cand &= cand - 1u;
+    const float4* tp = sc.tris + 3 * (size_t)i;
+    const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
+    if (COUNT) { tc.tris++; tc.flat_tris++; }
+    const float t = triangle_mt(f3(v0), f3(v1), f3(v2), o, d);
+    if (t >= 0.0f && t < best_t && tri_gate(sc, o, inv, i)) { best_t = t; best = i; }
+  }
+#endif
+#pragma unroll 1
+  for (int k = 0; k < (cand_loop_enabled() ? n_flat : 0); k++) {
     const float4* bp = sc.tri_box + 2 * (size_t)(sc.n_bvh_tris + k);
     const float4 lo = ldg4(bp + 0), hi = ldg4(bp + 1);
     if (lo.w == 0.0f) {                                            // warp-uniform: a new box

@@ -60,6 +60,10 @@ primary_kernel(const __grid_constant__ DevScene sc, int tiles_x, int tiles_y, fl
   else { const Surface s = surface_at(sc, o, d, t, id); prim[i] = s.prim; tout[i] = t; }
 }
 
+// RENDER_QUERY = false: the strict query (the reference's gate on every candidate).  true: the query exactly as the render
+// kernels run it (path_vertex.inc + the BVH phase): flat list, tree-bounds test, optimistic traversal (trav_step), the
+// nearest tree hit gated once, strict re-trace if the gate rejects it — so a replay divergence can be pinned on a ray.
+template <bool RENDER_QUERY>
 __global__ void __launch_bounds__(kBlockThreads)
 rays_kernel(const __grid_constant__ DevScene sc, long long n, const float* __restrict__ org, const float* __restrict__ dir,
             int* __restrict__ prim, float* __restrict__ tout, float* __restrict__ nout) {
@@ -69,7 +73,18 @@ rays_kernel(const __grid_constant__ DevScene sc, long long n, const float* __res
   float t;
   int id;
   TraceCounters tc;
-  trace<false>(sc, o, d, t, id, tc);
+  if (RENDER_QUERY) {
+    const F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    t = 3.0e38f;
+    id = -1;
+    flat_hits<false>(sc, o, d, inv, t, id, tc);
+    if (sc.n_nodes > 0 && bvh_bounds_hit(sc, o, inv, t < 3.0e38f ? t * 1.0001f + 1e-4f : 3.0e38f)) {
+      bvh_traverse_unified<false>(sc, o, d, inv, t, id, tc);
+      if (id >= 0 && id < sc.n_bvh_tris && !bvh_hit_is_gated(sc, o, inv, id)) trace<false>(sc, o, d, t, id, tc);
+    }
+  } else {
+    trace<false>(sc, o, d, t, id, tc);
+  }
   if (id == -1) {
     prim[i] = -1; tout[i] = 0.0f;
     if (nout) { nout[3 * i] = 0.0f; nout[3 * i + 1] = 0.0f; nout[3 * i + 2] = 0.0f; }
@@ -182,8 +197,11 @@ cudaError_t launch_aov(const DevScene& sc, const DevParams& p, int kind, float* 
   return cudaGetLastError();
 }
 
-cudaError_t launch_rays(const DevScene& sc, long long n, const float* org, const float* dir, int* prim, float* t, float* nout, cudaStream_t stream) {
-  rays_kernel<<<(unsigned int)((n + kBlockThreads - 1) / kBlockThreads), kBlockThreads, 0, stream>>>(sc, n, org, dir, prim, t, nout);
+cudaError_t launch_rays(const DevScene& sc, long long n, const float* org, const float* dir, int* prim, float* t, float* nout, bool render_query,
+                        cudaStream_t stream) {
+  const unsigned int blocks = (unsigned int)((n + kBlockThreads - 1) / kBlockThreads);
+  if (render_query) rays_kernel<true><<<blocks, kBlockThreads, 0, stream>>>(sc, n, org, dir, prim, t, nout);
+  else rays_kernel<false><<<blocks, kBlockThreads, 0, stream>>>(sc, n, org, dir, prim, t, nout);
   return cudaGetLastError();
 }
 

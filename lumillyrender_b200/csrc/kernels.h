@@ -23,7 +23,7 @@ cudaError_t launch_reduce_peers(float* dst, const PeerBuffers& src, size_t n, fl
 cudaError_t launch_primary(const DevScene& sc, float u, float v, float ua, float va, int* prim, float* t, cudaStream_t stream);
 cudaError_t launch_aov(const DevScene& sc, const DevParams& p, int kind, float* out, cudaStream_t stream);
 cudaError_t launch_rays(const DevScene& sc, long long n, const float* org, const float* dir, int* prim, float* t, float* nout,
-                        cudaStream_t stream);
+                        bool render_query, cudaStream_t stream);
 
 cudaError_t launch_read_bw(const float4* buf, size_t n4, int iters, int blocks, float* sink, cudaStream_t stream);
 }  // namespace lr

@@ -68,7 +68,7 @@ __host__ __device__ constexpr int words_per_slot(bool want_sumsq) {
   return (INTEGRATOR == LR_INTEGRATOR_PT_DIRECT ? (int)W_PTD_COUNT : (int)W_PT_COUNT) + (want_sumsq ? 3 : 0);
 }
 template <int INTEGRATOR>
-__host__ __device__ constexpr int warp_words(bool want_sumsq) { return words_per_slot<INTEGRATOR>(want_sumsq) * slots<INTEGRATOR>() + 32; }
+__host__ __device__ constexpr int warp_words(bool want_sumsq) { return words_per_slot<INTEGRATOR>(want_sumsq) * slots<INTEGRATOR>() + 64; }   // + the selection list
 
 // Takes the first `quota` set bits of the concatenation words[rot] | words[rot + 1] | ... (cyclic): their codes
 // word * 32 + bit go to list[0, n) in that order, the bits are cleared in `words`.  Returns n (warp-uniform).  Lane j
@@ -252,9 +252,58 @@ render_pool_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ 
       // at most one inner node and one triangle test per iteration (trav_step), optimistic accept, the nearest hit gated
       // once at the end, strict re-trace in the rare case the gate rejects it.  (Refilling idle lanes from the pool
       // inside this loop was measured too: the bookkeeping costs more than the width it keeps, profiles/r01_e_*.)
+#ifdef LR_POOL_B2
+      // Two rays per lane: a lane that holds two independent traversals has two node fetches in flight and idles only
+      // when BOTH are done — the BVH phase is bound by the latency of its dependent fetches and by the tail of its longest
+      // ray (9.6 of 32 lanes active with one ray per lane, profiles/r01_e_render_kernel_regions.txt).
+      const int n_sel = select_take<NR * kWords>(list, lane, pend, 64, rot_b);
+      rot_b = rot_b + 1 == NR * kWords ? 0 : rot_b + 1;
+      {
+        TravState ts[2];
+        int stk0[kStackDepth], stk1[kStackDepth];
+        int slot_of[2];
+        bool shadow_of[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          const bool on = lane + 32 * k < n_sel;
+          const int item = on ? list[lane + 32 * k] : 0;
+          const int s = item % (32 * kWords);
+          const bool shadow = NR == 2 && item >= 32 * kWords;
+          slot_of[k] = on ? s : -1;
+          shadow_of[k] = shadow;
+          ts[k].cur = kTravDone; ts[k].leaf_left = 0;
+          if (on) {
+            const F3 o = f3(SLF(W_OX), SLF(W_OY), SLF(W_OZ));
+            const F3 d = shadow ? f3(SLF(W_D1X), SLF(W_D1Y), SLF(W_D1Z)) : f3(SLF(W_DX), SLF(W_DY), SLF(W_DZ));
+            const F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+            trav_begin(ts[k], k == 0 ? stk0 : stk1, o, d, inv, shadow ? SLF(W_T1) : SLF(W_T0), shadow ? SLI(W_ID1) : SLI(W_ID0));
+          }
+        }
+        while (!trav_done(ts[0]) || !trav_done(ts[1])) {
+          if (!trav_done(ts[0])) trav_step<COUNT>(sc, ts[0], stk0, tc);
+          if (!trav_done(ts[1])) trav_step<COUNT>(sc, ts[1], stk1, tc);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          const int s = slot_of[k];
+          if (s >= 0) {
+            float t = ts[k].best_t;
+            int id = ts[k].best;
+            if (id >= 0 && id < sc.n_bvh_tris && !bvh_hit_is_gated(sc, ts[k].o, ts[k].inv, id)) {
+              t = shadow_of[k] ? SLF(W_T1) : SLF(W_T0); id = shadow_of[k] ? SLI(W_ID1) : SLI(W_ID0);   // the flat candidate the ray came with
+              trace_strict<COUNT>(sc, ts[k].o, ts[k].d, &t, &id, &tc);
+              n_retrace++;
+            }
+            if (shadow_of[k]) { SLF(W_T1) = t; SLI(W_ID1) = id; } else { SLF(W_T0) = t; SLI(W_ID0) = id; }
+          }
+        }
+      }
+      if (false) {
+#else
       const int n_sel = select_take<NR * kWords>(list, lane, pend, 32, rot_b);
       rot_b = rot_b + 1 == NR * kWords ? 0 : rot_b + 1;
       if (lane < n_sel) {
+#endif
         const int item = list[lane];                          // mask word * 32 + bit; the shadow rays' words follow the kWords extension words
         const int s = item % (32 * kWords);
         const bool shadow = NR == 2 && item >= 32 * kWords;

@@ -183,14 +183,16 @@ class Scene:
         check(self._lib.lr_trace_primary(self._s, u, v, ua, va, _iptr(prim), _fptr(t)))
         return prim, t
 
-    def trace_rays(self, origins, directions, normals=False):
+    def trace_rays(self, origins, directions, normals=False, render_query=False):
+        """Nearest hits of arbitrary rays: the strict query, or (render_query=True) the query as the render kernels run it."""
         o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
         d = np.ascontiguousarray(directions, dtype=np.float32).reshape(-1, 3)
         n = o.shape[0]
         prim = np.empty(n, dtype=np.int32)
         t = np.empty(n, dtype=np.float32)
         nrm = np.empty((n, 3), dtype=np.float32) if normals else None
-        check(self._lib.lr_trace_rays(self._s, n, _fptr(o), _fptr(d), _iptr(prim), _fptr(t), _fptr(nrm) if normals else None))
+        check(self._lib.lr_trace_rays_query(self._s, n, _fptr(o), _fptr(d), 1 if render_query else 0, _iptr(prim), _fptr(t),
+                                            _fptr(nrm) if normals else None))
         return (prim, t, nrm) if normals else (prim, t)
 
     def close(self):

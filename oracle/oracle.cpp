@@ -665,14 +665,18 @@ static bool brute_intersect(const SceneImpl& sc, const Ray& ray, Intersection& b
   return have;
 }
 
+struct RayRecord { Ray ray; int prim; float distance; };
 struct Tracer {
   const SceneImpl& sc;
   int traversal;
   Counters c;
+  std::vector<RayRecord>* record = nullptr;      // orc_trace_path: every closest-hit query of one sample, in order
   // Objects::intersect objects.rs:63-65
   bool intersect(const Ray& ray, Intersection& out) {
     c.rays++;
-    return traversal == 0 ? bvh_intersect_faithful(sc, ray, out, c) : bvh_intersect_fast(sc, ray, out, c);
+    const bool hit = traversal == 0 ? bvh_intersect_faithful(sc, ray, out, c) : bvh_intersect_fast(sc, ray, out, c);
+    if (record) record->push_back(RayRecord{ray, hit ? out.prim : -1, hit ? out.distance : 0.0f});
+    return hit;
   }
 };
 
@@ -1094,6 +1098,29 @@ int orc_render_aov(const OrcScene* s, const LrRenderParams* p, int kind, int tra
   std::vector<std::thread> th;
   for (int k = 0; k < n_threads; k++) th.emplace_back(worker);
   for (auto& k : th) k.join();
+  return LR_OK;
+}
+
+// Every closest-hit query (Objects::intersect, objects.rs:63-65) that ONE sample of one pixel issues, in order: camera ray,
+// then per vertex the shadow ray (pt-direct) and the extension ray — with what each hit.  A debugging probe for replay
+// divergences: the rays can be handed to the device's nearest-hit probes one by one.  Shared counter-based stream.
+int orc_trace_path(const OrcScene* s, const LrRenderParams* p, int x, int y, int sample, int traversal, int max_rays,
+                   float* origins, float* directions, int32_t* prim, float* t, int32_t* n_rays) {
+  if (!s || !p || !origins || !directions || !prim || !t || !n_rays) return LR_ERR_INVALID;
+  const SceneImpl& sc = s->impl;
+  if (x < 0 || y < 0 || x >= sc.camera.width || y >= sc.camera.height) return LR_ERR_INVALID;
+  g_math_mode = 1;
+  Rng rng;
+  std::vector<RayRecord> rec;
+  Integrator in{sc, Tracer{sc, traversal, Counters{}, &rec}, rng, p->depth, p->depth_limit, p->no_direct_emitter != 0};
+  rng.seed_counter(p->seed, (uint32_t)(y * sc.camera.width + x), (uint32_t)sample);
+  const CamSample cs = camera_sample(sc.camera, x, y, [&]() { return rng.next(); });
+  if (p->integrator == LR_INTEGRATOR_PT) in.radiance_recursive(cs.ray, 0); else in.radiance_nee_recursive(cs.ray, 0, false);
+  *n_rays = (int32_t)rec.size();
+  for (int i = 0; i < (int)rec.size() && i < max_rays; i++) {
+    to3(rec[i].ray.origin, origins + 3 * i); to3(rec[i].ray.direction, directions + 3 * i);
+    prim[i] = rec[i].prim; t[i] = rec[i].distance;
+  }
   return LR_OK;
 }
 

@@ -51,6 +51,10 @@ void orc_spec_sincos(float x, float* s, float* c);
  * camera rays of the sample range, averaged per pixel in sample order (shared counter-based stream). */
 int orc_render_aov(const OrcScene* s, const LrRenderParams* p, int kind, int traversal, int n_threads, float* out);
 
+/* every closest-hit query one sample of pixel (x, y) issues, in order, with its result (debugging probe) */
+int orc_trace_path(const OrcScene* s, const LrRenderParams* p, int x, int y, int sample, int traversal, int max_rays,
+                   float* origins, float* directions, int32_t* prim, float* t, int32_t* n_rays);
+
 int orc_trace_primary(const OrcScene* s, float u, float v, float ua, float va, int traversal,
                       int n_threads, int32_t* prim, float* t);
 int orc_trace_rays(const OrcScene* s, int64_t n, const float* origins, const float* directions,

@@ -47,6 +47,7 @@ def lib():
         L.orc_scene_nodes.argtypes = [C.c_void_p]
         L.orc_render.argtypes = [C.c_void_p, C.POINTER(LrRenderParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _PF, _PF, C.POINTER(OrcStats)]
         L.orc_render_aov.argtypes = [C.c_void_p, C.POINTER(LrRenderParams), C.c_int, C.c_int, C.c_int, _PF]
+        L.orc_trace_path.argtypes = [C.c_void_p, C.POINTER(LrRenderParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _PF, _PF, _PI, _PF, _PI]
         L.orc_set_math_mode.argtypes = [C.c_int]
         L.orc_spec_sincos.argtypes = [C.c_float, _PF, _PF]
         L.orc_trace_primary.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _PI, _PF]
@@ -136,6 +137,17 @@ class OracleScene:
         if rc != 0:
             raise RuntimeError("orc_render_aov failed: %d" % rc)
         return out
+
+    def trace_path(self, params, x, y, sample, traversal=0, max_rays=4096):
+        """(origins, directions, prim, t) of every closest-hit query one sample of pixel (x, y) issues, in order."""
+        o = np.zeros((max_rays, 3), np.float32); d = np.zeros((max_rays, 3), np.float32)
+        prim = np.zeros(max_rays, np.int32); t = np.zeros(max_rays, np.float32)
+        n = C.c_int32()
+        rc = self._L.orc_trace_path(self._s, C.byref(params), x, y, sample, traversal, max_rays, fp(o), fp(d), prim.ctypes.data_as(_PI), fp(t), C.byref(n))
+        if rc != 0:
+            raise RuntimeError("orc_trace_path failed: %d" % rc)
+        k = min(n.value, max_rays)
+        return o[:k], d[:k], prim[:k], t[:k]
 
     def trace_primary(self, u=0.5, v=0.5, ua=0.5, va=0.5, traversal=0, threads=0):
         prim = np.empty((self.height, self.width), dtype=np.int32)

@@ -16,9 +16,15 @@ else:
         i = args.index("--rounds")
         rounds = int(args[i + 1])
         del args[i:i + 2]
+    configs = None                       # --configs CFG ...: sweep.py configurations (LR_* knobs) run for every variant
+    if "--configs" in args:
+        i = args.index("--configs")
+        configs = args[i + 1:]
+        del args[i:]
     names = args
     for r in range(rounds):
         for n in names:
             env = dict(os.environ, LUMILLY_LIB=os.path.join(ROOT, "lumillyrender_b200", "variants", "lib_%s.so" % n))
-            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sweep.py"), n], env=env, capture_output=True, text=True)
+            cfgs = ["%s,%s" % (n, c) for c in configs] if configs else [n]
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sweep.py")] + cfgs, env=env, capture_output=True, text=True)
             print(out.stdout.strip() or out.stderr[-400:], flush=True)

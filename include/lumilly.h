@@ -221,6 +221,14 @@ int lr_shard_range(int32_t spp_begin, int32_t spp_count, int32_t part, int32_t n
 
 int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* params, int32_t n_devices, const int32_t* devices,
                     float* out_rgb, float* out_sumsq, LrStats* stats);
+/* The same as a handle, for a host that renders more than once (progressive previews, animations, a benchmark loop): the
+   scene is uploaded to every device, the per-device streams / events are made and the peer mappings that let devices[0]
+   read the others' film buffers are established ONCE (first use of a mapping costs ~100 ms per device pair);
+   lr_multi_render then only launches, reduces and copies.  lr_render_multi is create + render + destroy.            */
+typedef struct LrMultiScene LrMultiScene;
+int lr_multi_scene_create(const LrSceneDesc* desc, int32_t n_devices, const int32_t* devices, LrMultiScene** out);
+int lr_multi_render(LrMultiScene* ms, const LrRenderParams* params, float* out_rgb, float* out_sumsq, LrStats* stats);
+void lr_multi_scene_destroy(LrMultiScene* ms);
 
 /* ---- AOVs: Scene::normal / Scene::depth (src/scene.rs:48-62) of the camera ray of every sample in
  * [spp_begin, spp_begin + spp_count) — the very camera rays lr_render draws for those samples (same seed, same

@@ -109,6 +109,9 @@ SIGNATURES = {
     "lr_film_save": (C.c_int, [_VP, C.c_char_p]),
     "lr_film_load": (C.c_int, [_VP, C.c_char_p, C.POINTER(_VP)]),
     "lr_film_destroy": (None, [_VP]),
+    "lr_multi_scene_create": (C.c_int, [C.POINTER(LrSceneDesc), i32, _PI, C.POINTER(_VP)]),
+    "lr_multi_render": (C.c_int, [_VP, C.POINTER(LrRenderParams), _PF, _PF, C.POINTER(LrStats)]),
+    "lr_multi_scene_destroy": (None, [_VP]),
     "lr_trace_primary": (C.c_int, [_VP, f32, f32, f32, f32, _PI, _PF]),
     "lr_trace_rays": (C.c_int, [_VP, i64, _PF, _PF, _PI, _PF, _PF]),
     "lr_trace_rays_query": (C.c_int, [_VP, i64, _PF, _PF, i32, _PI, _PF, _PF]),

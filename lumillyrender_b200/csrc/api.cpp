@@ -546,11 +546,49 @@ static int scene_clone(const LrScene* src, int src_device, int dst_device, LrSce
   return LR_OK;
 }
 
-static int lr_render_multi_body(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_devices, const int32_t* devices, float* out_rgb,
-                    float* out_sumsq, LrStats* stats) {
-  if (!desc || !p || !devices || !out_rgb) return fail(LR_ERR_INVALID, "null argument");
+// ---------------------------------------------------------------- one process, several GPUs
+}  // extern "C"
+
+// The scene on every listed device, with everything a render needs set up ONCE: the clones, a non-blocking stream and a
+// completion event per device, the peer mappings that let devices[0] read the others' film buffers (pool access has a
+// first-use cost of ~100 ms per device pair: it was the "set-up spike" of calling lr_render_multi repeatedly).
+struct LrMultiScene {
+  int n = 0;
+  int devices[kMaxPeers] = {};
+  LrScene* scenes[kMaxPeers] = {};
+  cudaStream_t streams[kMaxPeers] = {};
+  cudaEvent_t done[kMaxPeers] = {};
+  bool mapped[kMaxPeers] = {};
+  float* staged = nullptr;                 // on devices[0]: copies of the film buffers it cannot map
+  size_t staged_floats = 0;
+  int home = 0;
+};
+
+namespace {
+
+// device i's stream-ordered pool grants `reader` access (plain cudaDeviceEnablePeerAccess covers cudaMalloc memory only)
+bool map_peer(int reader, int owner) {
+  int can = 0;
+  if (std::getenv("LR_MULTI_NO_PEER") != nullptr) return false;          // development / tests: force the staged path
+  if (cudaDeviceCanAccessPeer(&can, reader, owner) != cudaSuccess || !can) { cudaGetLastError(); return false; }
+  if (cudaSetDevice(reader) != cudaSuccess) return false;
+  const cudaError_t pe = cudaDeviceEnablePeerAccess(owner, 0);
+  if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return false; }
+  cudaGetLastError();
+  cudaMemPool_t pool;
+  cudaMemAccessDesc ad;
+  std::memset(&ad, 0, sizeof(ad));
+  ad.location.type = cudaMemLocationTypeDevice;
+  ad.location.id = reader;
+  ad.flags = cudaMemAccessFlagsProtReadWrite;
+  if (cudaDeviceGetDefaultMemPool(&pool, owner) != cudaSuccess || cudaMemPoolSetAccess(pool, &ad, 1) != cudaSuccess) { cudaGetLastError(); return false; }
+  return true;
+}
+
+int multi_create(const LrSceneDesc* desc, int32_t n_devices, const int32_t* devices, LrMultiScene** out) {
+  if (!desc || !devices || !out) return fail(LR_ERR_INVALID, "null argument");
+  *out = nullptr;
   if (n_devices < 1 || n_devices > kMaxPeers) return fail(LR_ERR_INVALID, "lr_render_multi takes 1..8 devices");
-  if (p->spp_count <= 0 || p->spp_begin < 0) return fail(LR_ERR_INVALID, "spp range must be non-empty and non-negative");
   int n_visible = 0;
   if (cudaGetDeviceCount(&n_visible) != cudaSuccess || n_visible <= 0)
     return fail(LR_ERR_NO_DEVICE, "no CUDA device available; liblumilly_b200 has no CPU fallback");
@@ -560,126 +598,123 @@ static int lr_render_multi_body(const LrSceneDesc* desc, const LrRenderParams* p
   }
   int prev_device = 0;
   cudaGetDevice(&prev_device);
-  const int home = g_device >= 0 ? g_device : devices[0];
+  LrMultiScene* m = new LrMultiScene();
+  m->n = n_devices;
+  m->home = g_device >= 0 ? g_device : devices[0];
+  for (int i = 0; i < n_devices; i++) m->devices[i] = devices[i];
+  int rc = LR_OK;
+  // scenes first: the first device gets the scene from the host, the others a device-to-device copy of its packed block
+  for (int i = 0; i < n_devices && rc == LR_OK; i++) {
+    if ((rc = lr_init(devices[i])) != LR_OK) break;          // cudaSetDevice + the non-trimming memory pool
+    if ((rc = i == 0 ? lr_scene_create(desc, &m->scenes[0]) : scene_clone(m->scenes[0], devices[0], devices[i], &m->scenes[i])) != LR_OK) break;
+    cudaError_t e = cudaStreamCreateWithFlags(&m->streams[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->done[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);      // the clone has landed
+    if (e != cudaSuccess) rc = fail(LR_ERR_CUDA, std::string("lr_multi_scene_create: ") + cudaGetErrorString(e));
+  }
+  m->mapped[0] = true;
+  for (int i = 1; i < n_devices && rc == LR_OK; i++) m->mapped[i] = map_peer(devices[0], devices[i]);
+  cudaSetDevice(m->home >= 0 && m->home < n_visible ? m->home : prev_device);
+  g_device = m->home;
+  if (rc != LR_OK) {
+    const std::string err = g_error;
+    lr_multi_scene_destroy(m);
+    g_error = err;
+    return rc;
+  }
+  *out = m;
+  return LR_OK;
+}
+
+int multi_render(LrMultiScene* m, const LrRenderParams* p, float* out_rgb, float* out_sumsq, LrStats* stats) {
+  if (!m || !p || !out_rgb) return fail(LR_ERR_INVALID, "null argument");
+  if (p->spp_count <= 0 || p->spp_begin < 0) return fail(LR_ERR_INVALID, "spp range must be non-empty and non-negative");
+  const int n_devices = m->n;
   // LR_MULTI_TRACE=1: wall-clock milliseconds of each phase on stderr (development)
   const bool trace_on = std::getenv("LR_MULTI_TRACE") != nullptr;
   auto t_prev = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
     if (!trace_on) return;
     const auto now = std::chrono::steady_clock::now();
-    std::fprintf(stderr, "lr_render_multi %-8s %8.2f ms\n", what, std::chrono::duration<float, std::milli>(now - t_prev).count());
+    std::fprintf(stderr, "lr_multi_render %-10s %8.2f ms\n", what, std::chrono::duration<float, std::milli>(now - t_prev).count());
     t_prev = now;
   };
-
-  std::vector<LrScene*> scenes(n_devices, nullptr);
-  std::vector<LrRenderParams> parts(n_devices, *p);
-  std::vector<cudaEvent_t> done(n_devices, nullptr);
-  float* staged = nullptr;                                 // on devices[0]: copies of buffers it cannot map
+  LrRenderParams parts[kMaxPeers];
   size_t n = 0;
   int rc = LR_OK;
   LrStats total;
   std::memset(&total, 0, sizeof(total));
   do {
-    // ---- scenes first: the first device gets the scene from the host, the others a device-to-device copy of its packed
-    // block.  (A peer copy in the default stream waits for the work queued on BOTH devices, so no render may be running
-    // yet: with the copies interleaved between the launches the devices rendered one after the other.)
+    // ---- launch: asynchronous on every device's own stream, so the devices render concurrently
     for (int i = 0; i < n_devices && rc == LR_OK; i++) {
-      if ((rc = lr_init(devices[i])) != LR_OK) break;      // cudaSetDevice + the non-trimming memory pool
-      if ((rc = i == 0 ? lr_scene_create(desc, &scenes[0]) : scene_clone(scenes[0], devices[0], devices[i], &scenes[i])) != LR_OK) break;
-      const LrScene* s = scenes[i];
+      cudaError_t e = cudaSetDevice(m->devices[i]);
+      if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); break; }
+      g_device = m->devices[i];
+      const LrScene* s = m->scenes[i];
+      parts[i] = *p;
       if ((rc = lr_shard_range(p->spp_begin, p->spp_count, i, n_devices, &parts[i].spp_begin, &parts[i].spp_count)) != LR_OK) break;
       DevParams dp;
       LrRenderParams probe = parts[i];
-      if (probe.spp_count == 0) probe.spp_count = 1;       // more devices than samples: this one only contributes zeros
+      if (probe.spp_count == 0) probe.spp_count = 1;         // more devices than samples: this one only contributes zeros
       if ((rc = resolve_params(s, &probe, dp)) != LR_OK) break;
       n = (size_t)dp.crop_w * dp.crop_h * 3;
       if ((rc = ensure_scratch(&s->d_film, &s->film_floats, n)) != LR_OK) break;
       if (out_sumsq && (rc = ensure_scratch(&s->d_film_sq, &s->film_sq_floats, n)) != LR_OK) break;
-      cudaError_t e = cudaMemsetAsync(s->d_film, 0, n * sizeof(float), 0);
-      if (e == cudaSuccess && out_sumsq) e = cudaMemsetAsync(s->d_film_sq, 0, n * sizeof(float), 0);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(0);  // the copy has landed before anything is launched anywhere
-      if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("lr_render_multi set-up: ") + cudaGetErrorString(e)); break; }
-    }
-    lap("set-up");
-    // ---- launch: asynchronous, so the devices render concurrently
-    for (int i = 0; i < n_devices && rc == LR_OK; i++) {
-      cudaError_t e = cudaSetDevice(devices[i]);
-      if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); break; }
-      const LrScene* s = scenes[i];
+      e = cudaMemsetAsync(s->d_film, 0, n * sizeof(float), m->streams[i]);
+      if (e == cudaSuccess && out_sumsq) e = cudaMemsetAsync(s->d_film_sq, 0, n * sizeof(float), m->streams[i]);
+      if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("lr_multi_render set-up: ") + cudaGetErrorString(e)); break; }
       if (parts[i].spp_count > 0 &&
-          (rc = lr_render_accumulate_device(s, &parts[i], s->d_film, out_sumsq ? s->d_film_sq : nullptr, nullptr)) != LR_OK) break;
-      e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
-      if (e == cudaSuccess) e = cudaEventRecord(done[i], 0);
+          (rc = lr_render_accumulate_device(s, &parts[i], s->d_film, out_sumsq ? s->d_film_sq : nullptr, m->streams[i])) != LR_OK) break;
+      e = cudaEventRecord(m->done[i], m->streams[i]);
       if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("cudaEventRecord: ") + cudaGetErrorString(e)); break; }
     }
     if (rc != LR_OK) break;
     lap("launch");
 
-    // ---- reduce + normalise on devices[0]
-    cudaError_t e = cudaSetDevice(devices[0]);
+    // ---- reduce + normalise on devices[0]: one kernel reads every device's sums (peer access over NVLink; a staged copy
+    // where a peer cannot be mapped), adds them in list order and divides by spp (main.rs:104)
+    cudaError_t e = cudaSetDevice(m->devices[0]);
+    g_device = m->devices[0];
+    cudaStream_t st0 = m->streams[0];
     PeerBuffers sum_src, sq_src;
     sum_src.count = sq_src.count = n_devices;
-    size_t staged_floats = 0;
-    std::vector<int> mapped(n_devices, 1);
-    const bool no_peer = std::getenv("LR_MULTI_NO_PEER") != nullptr;      // development / tests: force the staged path
-    static bool pool_mapped[64][64] = {};                                // [reader][owner]: the owner's pool already grants the reader access
-    for (int i = 1; i < n_devices && e == cudaSuccess; i++) {
-      int can = 0;
-      if (!no_peer) cudaDeviceCanAccessPeer(&can, devices[0], devices[i]);
-      if (can) {
-        // the film buffers come from device i's stream-ordered pool: the pool must grant devices[0] access (plain
-        // cudaDeviceEnablePeerAccess covers cudaMalloc memory only)
-        const cudaError_t pe = cudaDeviceEnablePeerAccess(devices[i], 0);
-        if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
-        else if (pe != cudaSuccess) { can = 0; cudaGetLastError(); }
-        cudaMemPool_t pool;
-        cudaMemAccessDesc ad;
-        std::memset(&ad, 0, sizeof(ad));
-        ad.location.type = cudaMemLocationTypeDevice;
-        ad.location.id = devices[0];
-        ad.flags = cudaMemAccessFlagsProtReadWrite;
-        const bool known = devices[0] < 64 && devices[i] < 64 && pool_mapped[devices[0]][devices[i]];
-        if (can && !known) {
-          if (cudaDeviceGetDefaultMemPool(&pool, devices[i]) != cudaSuccess || cudaMemPoolSetAccess(pool, &ad, 1) != cudaSuccess) {
-            can = 0;
-            cudaGetLastError();
-          } else if (devices[0] < 64 && devices[i] < 64) {
-            pool_mapped[devices[0]][devices[i]] = true;
-          }
-        }
-      }
-      mapped[i] = can;
-      if (!can) staged_floats += n * (out_sumsq ? 2 : 1);
+    size_t need_staged = 0;
+    for (int i = 1; i < n_devices; i++) if (!m->mapped[i]) need_staged += n * (out_sumsq ? 2 : 1);
+    if (e == cudaSuccess && need_staged > m->staged_floats) {
+      dev_free(m->staged);
+      m->staged = nullptr; m->staged_floats = 0;
+      e = dev_alloc((void**)&m->staged, need_staged * sizeof(float));
+      if (e == cudaSuccess) m->staged_floats = need_staged;
     }
-    if (e == cudaSuccess && staged_floats > 0) e = dev_alloc((void**)&staged, staged_floats * sizeof(float));
-    float* stage_next = staged;
+    float* stage_next = m->staged;
     for (int i = 0; i < n_devices && e == cudaSuccess; i++) {
-      e = cudaStreamWaitEvent(0, done[i], 0);              // devices[0]'s stream waits for device i's render
+      if (i > 0) e = cudaStreamWaitEvent(st0, m->done[i], 0);     // devices[0]'s stream waits for device i's render
       if (e != cudaSuccess) break;
-      sum_src.p[i] = scenes[i]->d_film;
-      sq_src.p[i] = out_sumsq ? scenes[i]->d_film_sq : nullptr;
-      if (!mapped[i]) {
-        e = cudaMemcpyPeerAsync(stage_next, devices[0], scenes[i]->d_film, devices[i], n * sizeof(float), 0);
+      sum_src.p[i] = m->scenes[i]->d_film;
+      sq_src.p[i] = out_sumsq ? m->scenes[i]->d_film_sq : nullptr;
+      if (!m->mapped[i]) {
+        e = cudaMemcpyPeerAsync(stage_next, m->devices[0], m->scenes[i]->d_film, m->devices[i], n * sizeof(float), st0);
         sum_src.p[i] = stage_next; stage_next += n;
         if (e == cudaSuccess && out_sumsq) {
-          e = cudaMemcpyPeerAsync(stage_next, devices[0], scenes[i]->d_film_sq, devices[i], n * sizeof(float), 0);
+          e = cudaMemcpyPeerAsync(stage_next, m->devices[0], m->scenes[i]->d_film_sq, m->devices[i], n * sizeof(float), st0);
           sq_src.p[i] = stage_next; stage_next += n;
         }
       }
     }
-    lap("peers");
-    if (e == cudaSuccess) e = launch_reduce_peers(scenes[0]->d_film, sum_src, n, (float)p->spp_count, 0);   // main.rs:104
-    if (e == cudaSuccess && out_sumsq) e = launch_reduce_peers(scenes[0]->d_film_sq, sq_src, n, 0.0f, 0);
-    if (e == cudaSuccess) e = cudaMemcpy(out_rgb, scenes[0]->d_film, n * sizeof(float), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && out_sumsq) e = cudaMemcpy(out_sumsq, scenes[0]->d_film_sq, n * sizeof(float), cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("lr_render_multi reduce: ") + cudaGetErrorString(e)); break; }
-
+    if (e == cudaSuccess) e = launch_reduce_peers(m->scenes[0]->d_film, sum_src, n, (float)p->spp_count, st0);   // main.rs:104
+    if (e == cudaSuccess && out_sumsq) e = launch_reduce_peers(m->scenes[0]->d_film_sq, sq_src, n, 0.0f, st0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_rgb, m->scenes[0]->d_film, n * sizeof(float), cudaMemcpyDeviceToHost, st0);
+    if (e == cudaSuccess && out_sumsq) e = cudaMemcpyAsync(out_sumsq, m->scenes[0]->d_film_sq, n * sizeof(float), cudaMemcpyDeviceToHost, st0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st0);
+    if (e != cudaSuccess) { rc = fail(LR_ERR_CUDA, std::string("lr_multi_render reduce: ") + cudaGetErrorString(e)); break; }
     lap("render+d2h");
+
     // ---- statistics: totals over the devices, the slowest device's kernel time
     for (int i = 0; i < n_devices && rc == LR_OK; i++) {
-      if (cudaSetDevice(devices[i]) != cudaSuccess) { rc = fail(LR_ERR_CUDA, "cudaSetDevice failed"); break; }
+      if (cudaSetDevice(m->devices[i]) != cudaSuccess) { rc = fail(LR_ERR_CUDA, "cudaSetDevice failed"); break; }
+      g_device = m->devices[i];
       LrStats st;
-      if ((rc = lr_stats_fetch(scenes[i], nullptr, &st)) != LR_OK) break;
+      if ((rc = lr_stats_fetch(m->scenes[i], m->streams[i], &st)) != LR_OK) break;
       total.rays += st.rays; total.samples += st.samples; total.nodes_visited += st.nodes_visited; total.tris_tested += st.tris_tested;
       total.spheres_tested += st.spheres_tested; total.nonfinite_samples += st.nonfinite_samples; total.gate_retraces += st.gate_retraces;
       total.flat_tris_tested += st.flat_tris_tested; total.flat_boxes_tested += st.flat_boxes_tested;
@@ -689,26 +724,57 @@ static int lr_render_multi_body(const LrSceneDesc* desc, const LrRenderParams* p
     }
     total.launches += out_sumsq ? 2 : 1;
   } while (0);
-
-  const std::string err = g_error;                         // clean-up must not clobber the message
-  for (int i = 0; i < n_devices; i++) {
-    if (!scenes[i] && !done[i]) continue;
-    cudaSetDevice(devices[i]);
-    cudaDeviceSynchronize();
-    if (done[i]) cudaEventDestroy(done[i]);
-    if (i == 0 && staged) dev_free(staged);
-    lr_scene_destroy(scenes[i]);
-  }
-  cudaSetDevice(home >= 0 && home < n_visible ? home : prev_device);
-  g_device = home;
-  lap("clean-up");
+  const std::string err = g_error;
+  if (rc != LR_OK) for (int i = 0; i < n_devices; i++) { cudaSetDevice(m->devices[i]); cudaDeviceSynchronize(); }   // nothing of this call stays in flight
+  cudaSetDevice(m->home);
+  g_device = m->home;
+  lap("stats");
   if (rc != LR_OK) { g_error = err; return rc; }
   if (stats) *stats = total;
   return LR_OK;
 }
+
+}  // namespace
+
+extern "C" {
+
+int lr_multi_scene_create(const LrSceneDesc* desc, int32_t n_devices, const int32_t* devices, LrMultiScene** out) {
+  LR_GUARDED(multi_create(desc, n_devices, devices, out));
+}
+
+int lr_multi_render(LrMultiScene* m, const LrRenderParams* p, float* out_rgb, float* out_sumsq, LrStats* stats) {
+  LR_GUARDED(multi_render(m, p, out_rgb, out_sumsq, stats));
+}
+
+void lr_multi_scene_destroy(LrMultiScene* m) {
+  if (!m) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (int i = 0; i < m->n; i++) {
+    if (!m->scenes[i] && !m->streams[i] && !m->done[i]) continue;
+    cudaSetDevice(m->devices[i]);
+    cudaDeviceSynchronize();
+    if (i == 0 && m->staged) dev_free(m->staged);
+    lr_scene_destroy(m->scenes[i]);
+    if (m->done[i]) cudaEventDestroy(m->done[i]);
+    if (m->streams[i]) cudaStreamDestroy(m->streams[i]);
+  }
+  cudaSetDevice(prev);
+  delete m;
+}
+
+// one-shot form: set-up, one render, tear-down
 int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_devices, const int32_t* devices, float* out_rgb,
                     float* out_sumsq, LrStats* stats) {
-  LR_GUARDED(lr_render_multi_body(desc, p, n_devices, devices, out_rgb, out_sumsq, stats));
+  if (!desc || !p || !devices || !out_rgb) return fail(LR_ERR_INVALID, "null argument");
+  if (p->spp_count <= 0 || p->spp_begin < 0) return fail(LR_ERR_INVALID, "spp range must be non-empty and non-negative");
+  LrMultiScene* m = nullptr;
+  if (int rc = lr_multi_scene_create(desc, n_devices, devices, &m)) return rc;
+  const int rc = lr_multi_render(m, p, out_rgb, out_sumsq, stats);
+  const std::string err = g_error;
+  lr_multi_scene_destroy(m);
+  g_error = err;
+  return rc;
 }
 
 int lr_trace_primary(const LrScene* s, float u, float v, float ua, float va, int32_t* prim, float* t) {

@@ -102,6 +102,10 @@ class Description:
         check(self._lib.lr_render_multi(self.desc, C.byref(p), len(devices), dev, _fptr(img), _fptr(sq) if sumsq else None, C.byref(st)))
         return img, sq, st.as_dict()
 
+    def multi_scene(self, devices):
+        """The scene on several GPUs of this box, set up once (lr_multi_scene_create): see MultiScene."""
+        return MultiScene(self, devices)
+
     def close(self):
         if self._h:
             self._lib.lr_host_scene_free(self._h)
@@ -199,6 +203,39 @@ class Scene:
         if self._s:
             self._lib.lr_scene_destroy(self._s)
             self._s = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiScene:
+    """One process, several GPUs (lr_multi_scene_create / lr_multi_render): scenes, streams and peer mappings are made once,
+    `render` shards the sample range over the devices and returns what Scene.render returns."""
+
+    def __init__(self, description, devices):
+        self._lib = capi.load_library()
+        self.description = description
+        self.config = description.config
+        self._m = C.c_void_p()
+        dev = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        check(self._lib.lr_multi_scene_create(description.desc, len(devices), dev, C.byref(self._m)))
+
+    def render(self, sumsq=False, **kw):
+        p = kw.pop("params", None) or params_from_config(self.config, **kw)
+        shape = (p.crop_h, p.crop_w, 3) if p.crop_w > 0 else (self.config.height, self.config.width, 3)
+        img = np.empty(shape, dtype=np.float32)
+        sq = np.empty(shape, dtype=np.float32) if sumsq else None
+        st = LrStats()
+        check(self._lib.lr_multi_render(self._m, C.byref(p), _fptr(img), _fptr(sq) if sumsq else None, C.byref(st)))
+        return img, sq, st.as_dict()
+
+    def close(self):
+        if self._m:
+            self._lib.lr_multi_scene_destroy(self._m)
+            self._m = C.c_void_p()
 
     def __del__(self):
         try:

@@ -254,6 +254,12 @@ def test_render_multi_single_process(scenes, lr, gpu, monkeypatch):
     ref, ref_sq, st = s.render(spp=6, seed=13, splits=1, sumsq=True)
     one, one_sq, st1 = d.render_multi([0], spp=6, seed=13, splits=1, sumsq=True)
     assert np.array_equal(one, ref) and np.array_equal(one_sq, ref_sq) and st1["rays"] == st["rays"] and st1["samples"] == st["samples"]
+    ms1 = d.multi_scene([0])
+    a1, _, sta = ms1.render(spp=6, seed=13, splits=1)
+    b1, _, _ = ms1.render(spp=3, spp_begin=3, seed=13, splits=1)
+    hi3, _, _ = s.render(spp=3, spp_begin=3, seed=13, splits=1)
+    assert np.array_equal(a1, ref) and sta["rays"] == st["rays"] and np.array_equal(b1, hi3)
+    ms1.close()
     with pytest.raises(LumillyError):
         d.render_multi([0, 0], spp=2)
     with pytest.raises(LumillyError):
@@ -282,6 +288,14 @@ def test_render_multi_single_process(scenes, lr, gpu, monkeypatch):
     few, _, stf = d.render_multi([1, 0], spp=1, seed=13, splits=1)
     solo, _, sts = s.render(spp=1, seed=13, splits=1)
     assert np.array_equal(few, solo) and stf["rays"] == sts["rays"]
+    # the handle form (scenes, streams, peer mappings set up once): same bits as the one-shot call, call after call
+    ms = d.multi_scene([0, 1])
+    for _ in range(3):
+        h, h_sq, sth = ms.render(spp=6, seed=13, splits=1, sumsq=True)
+        assert np.array_equal(h, two) and np.array_equal(h_sq, two_sq) and sth["rays"] == st["rays"]
+    hc, _, _ = ms.render(spp=6, seed=13, splits=1, crop=(37, 21, 50, 33))
+    assert np.array_equal(hc, two[21:21 + 33, 37:37 + 50])
+    ms.close()
 
 
 @pytest.mark.parametrize("sphere_light", [0.0, 8.0])

@@ -26,6 +26,19 @@ while n <= n_max:
     if ref is None:
         ref = img
     err = float(np.abs(img - ref).max())
+    # the handle form: set-up once, then renders only (what a host that renders more than once pays per render)
+    t0 = time.perf_counter()
+    ms = d.multi_scene(list(range(n)))
+    setup = time.perf_counter() - t0
+    walls = []
+    for rep in range(5):
+        t0 = time.perf_counter()
+        h, _, sth = ms.render(spp=spp, seed=rep)
+        walls.append(time.perf_counter() - t0)
+    ms.close()
+    print("lr_multi_render    N=%d spp=%d: set-up %.1f ms once, then per render min %.1f / median %.1f / max %.1f ms (%.0f Msamples/s at the median), "
+          "slowest kernel %.1f ms" % (n, spp, setup * 1e3, min(walls) * 1e3, sorted(walls)[2] * 1e3, max(walls) * 1e3,
+                                      sth["samples"] / sorted(walls)[2] / 1e6, sth["kernel_ms"]), flush=True)
     print("lr_render_multi N=%d spp=%d: wall %.1f ms (%.0f Msamples/s end to end, scene upload + render + reduce + D2H), slowest kernel %.1f ms, "
           "rays %d, max |diff| vs N=1 %.3g" % (n, spp, best[0] * 1e3, st["samples"] / best[0] / 1e6, best[1]["kernel_ms"], st["rays"], err), flush=True)
     n *= 2

@@ -174,6 +174,19 @@ LR_DEV bool ref_slab_pass_select(F3 lo, F3 hi, F3 o, F3 inv) {
   return !(mn > mx);
 }
 
+// ------------------------------------------------------------------ the tie rule
+// Two primitives can answer with bit-identical distances (a ray through a shared vertex or edge of a mesh).  The reference
+// keeps the first such candidate in the depth-first order of ITS tree (min_by, bvh.rs:136-140) — an order only its own SAH
+// build defines.  The device's trees differ from it and from each other (host SAH, device radix tree, flat list), so the
+// device rule is: among equal distances the LOWEST PRIMITIVE ID wins.  The nearest hit is then a function of the scene
+// alone — argmin over the valid candidates of (t, prim_id) — whatever the tree, the visiting order or the scheduling.
+// `best` is a candidate code: >= 0 triangle index, <= -2 sphere index = -2 - id (never -1 here: t == best_t implies a hit).
+static __device__ __noinline__ bool tie_goes_to(const float4* __restrict__ tris, const int2* __restrict__ sphere_meta, int cand_prim, int best) {
+  const int best_prim = best >= 0 ? __float_as_int(__ldg(tris + 3 * (size_t)best).w) : __ldg(sphere_meta + (-2 - best)).y;
+  return cand_prim < best_prim;
+}
+#define LR_NEARER(sc, t, cand_prim, best_t, best) ((t) < (best_t) || ((t) == (best_t) && tie_goes_to((sc).tris, (sc).sphere_meta, (cand_prim), (best))))
+
 struct TraceCounters { unsigned int nodes, tris, spheres, flat_tris, flat_boxes; };
 
 LR_DEV float4 ldg4(const float4* p) { return __ldg(p); }
@@ -191,7 +204,7 @@ LR_DEV bool tri_gate(const DevScene& sc, F3 o, F3 inv, int id) {
 //
 // Flat triangles go through the reference's own two steps in the reference's order: Leaf::may_intersect — the line-slab
 // test on the triangle's own box (bvh.rs:21-25, aabb.rs:75-92) — selects the candidates, then the primitive test runs on
-// those alone, in index order with a strict `<` (the first minimum wins, bvh.rs:136-140).  The gate is what makes a
+// those alone (nearest wins; among equal distances the lowest primitive id: the tie rule above).  The gate is what makes a
 // candidate valid, so testing it first is exact by construction; it is also cheap and selective: the line of a ray inside
 // a room crosses the (flat) boxes of two walls, so a lane runs Moller-Trumbore on ~4-6 of the ~12-16 flat triangles.
 //   * lanes hold DIFFERENT candidates in the second loop (a bit mask per lane, lowest bit first): the loop is as long as the
@@ -211,7 +224,7 @@ LR_DEV void flat_hits(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, int
     const float4 s = ldg4(sc.spheres + i);
     if (COUNT) tc.spheres++;
     const float t = sphere_hit(f3(s), s.w, o, d);
-    if (t >= 0.0f && t < best_t) {
+    if (t >= 0.0f && LR_NEARER(sc, t, __ldg(sc.sphere_meta + i).y, best_t, best)) {
       const F3 c = f3(s);
       const F3 r = f3(s.w, s.w, s.w);
       if (ref_slab_pass(c - r, c + r, o, inv)) { best_t = t; best = -2 - i; }
@@ -231,7 +244,7 @@ LR_DEV void flat_hits(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, int
     const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
     if (COUNT) { tc.tris++; tc.flat_tris++; }
     const float t = triangle_mt(f3(v0), f3(v1), f3(v2), o, d);
-    if (t >= 0.0f && t < best_t && tri_gate(sc, o, inv, i)) { best_t = t; best = i; }
+    if (t >= 0.0f && LR_NEARER(sc, t, __float_as_int(v0.w), best_t, best) && tri_gate(sc, o, inv, i)) { best_t = t; best = i; }
   }
 #endif
 #pragma unroll 1
@@ -252,7 +265,7 @@ LR_DEV void flat_hits(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, int
     const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
     if (COUNT) { tc.tris++; tc.flat_tris++; }
     const float t = triangle_mt(f3(v0), f3(v1), f3(v2), o, d);
-    if (t >= 0.0f && t < best_t) { best_t = t; best = i; }
+    if (t >= 0.0f && LR_NEARER(sc, t, __float_as_int(v0.w), best_t, best)) { best_t = t; best = i; }
   }
 }
 
@@ -321,7 +334,7 @@ LR_DEV void bvh_traverse(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, 
         const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
         if (COUNT) tc.tris++;
         const float t = triangle_mt(f3(v0), f3(v1), f3(v2), o, d);
-        if (t >= 0.0f && t < best_t) {
+        if (t >= 0.0f && LR_NEARER(sc, t, __float_as_int(v0.w), best_t, best)) {
           // the leaf's own AABB gate (triangle.rs:102-119 box, aabb.rs:75-92 test)
           if (tri_gate(sc, o, inv, first + k)) {
             best_t = t;
@@ -404,7 +417,7 @@ LR_DEV void trav_step(const DevScene& sc, TravState& s, int* stack, TraceCounter
     const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
     if (COUNT) tc.tris++;
     const float t = triangle_mt(f3(v0), f3(v1), f3(v2), s.o, s.d);
-    if (t >= 0.0f && t < s.best_t) {
+    if (t >= 0.0f && LR_NEARER(sc, t, __float_as_int(v0.w), s.best_t, s.best)) {
       s.best_t = t;
       s.best = s.leaf_first;
       s.cull_t = t * 1.0001f + 1e-4f;
@@ -425,7 +438,7 @@ LR_DEV void bvh_traverse_unified(const DevScene& sc, F3 o, F3 d, F3 inv, float& 
 
 LR_DEV bool bvh_hit_is_gated(const DevScene& sc, F3 o, F3 inv, int id) { return tri_gate(sc, o, inv, id); }
 
-// Nearest hit: flat candidates first, then the BVH (strict `<`, so on exact ties the earlier candidate stays).
+// Nearest hit: flat candidates first, then the BVH; among equal distances the lowest primitive id wins (the tie rule above).
 template <bool COUNT>
 LR_DEV void trace(const DevScene& sc, F3 o, F3 d, float& t_out, int& id_out, TraceCounters& tc) {
   const F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);

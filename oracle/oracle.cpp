@@ -584,7 +584,13 @@ static void may_intersect(const SceneImpl& sc, int node, const Ray& ray, std::ve
 }
 
 // bvh.rs:131-141 — candidates in DFS order, first minimum distance wins (Iterator::min_by)
-static bool bvh_intersect_faithful(const SceneImpl& sc, const Ray& ray, Intersection& best, Counters& c) {
+// tie_by_index = false: the reference's rule — among candidates at the same distance the FIRST in the depth-first order of
+// its tree wins (min_by keeps the first minimum, bvh.rs:136-140).  That order is a property of the reference's own SAH
+// build.  tie_by_index = true: the lowest primitive index wins instead — the rule of the device path, whose trees differ
+// from the reference's (and from each other: host SAH / device radix tree); it makes the nearest hit a function of the
+// scene alone.  The two rules differ only when two primitives answer with bit-identical distances (rays through shared
+// vertices / edges of a mesh).
+static bool bvh_intersect_faithful(const SceneImpl& sc, const Ray& ray, Intersection& best, Counters& c, bool tie_by_index = false) {
   if (sc.bvh.root < 0) return false;
   std::vector<int> candidate;
   may_intersect(sc, sc.bvh.root, ray, candidate, c);
@@ -595,7 +601,7 @@ static bool bvh_intersect_faithful(const SceneImpl& sc, const Ray& ray, Intersec
     if (!prim_intersect(sc.prims[i], ray, it)) continue;
     it.prim = i;
     if (std::isnan(it.distance)) continue;   // the reference panics here (partial_cmp().unwrap()); treated as a miss
-    if (!have || it.distance < best.distance) { best = it; have = true; }
+    if (!have || it.distance < best.distance || (tie_by_index && it.distance == best.distance && i < best.prim)) { best = it; have = true; }
   }
   return have;
 }
@@ -674,7 +680,9 @@ struct Tracer {
   // Objects::intersect objects.rs:63-65
   bool intersect(const Ray& ray, Intersection& out) {
     c.rays++;
-    const bool hit = traversal == 0 ? bvh_intersect_faithful(sc, ray, out, c) : bvh_intersect_fast(sc, ray, out, c);
+    // traversal 0: the reference's algorithm and tie rule; 1: pruned near-to-far walk (same hits; fast);
+    // 2: the reference's algorithm with the device's tie rule (lowest primitive index among equal distances)
+    const bool hit = traversal == 1 ? bvh_intersect_fast(sc, ray, out, c) : bvh_intersect_faithful(sc, ray, out, c, traversal == 2);
     if (record) record->push_back(RayRecord{ray, hit ? out.prim : -1, hit ? out.distance : 0.0f});
     return hit;
   }

@@ -126,14 +126,15 @@ def test_random_rays_match_faithful_traversal_on_the_real_tree(full, case):
     assert np.array_equal(ng[both], no[both]), "hit normals must be bit-identical"
 
 
-@pytest.mark.parametrize("case", ["sample-144k"])
+@pytest.mark.parametrize("case", ["sample-144k", "welcome-1M"])
 def test_rays_through_shared_vertices_tie_in_t(full, case):
-    """Rays aimed exactly at mesh vertices: the triangles around the vertex can answer with the SAME t (bit for bit), and the
-    reference keeps the first such candidate in the depth-first order of ITS tree (min_by, bvh.rs:136-140) — an order only
-    the reference's own SAH build defines (the oracle restates that build; its brute-force order already differs).  The
-    device keeps the first candidate in its own traversal order.  What must hold: the distance is the reference's bit for
-    bit on every ray, and the index differs only where the two winners tie in t.  (Measured: 0.7 % of such rays tie; a ray
-    drawn from a continuous distribution never does — the full-film probes above agree on 100 % of 2.6 M pixels.)"""
+    """Rays aimed exactly at mesh vertices: the triangles around the vertex can answer with the SAME t (bit for bit).  The
+    reference keeps the first such candidate in the depth-first order of ITS tree (min_by, bvh.rs:136-140) — an order only the
+    reference's own SAH build defines (the oracle restates that build).  The device's rule is topology-independent: among
+    equal distances the lowest primitive id wins, which is the order of the oracle's brute-force loop.  What must hold:
+    against the brute-force oracle EVERYTHING is equal (index, t, normal), ties included, for both device queries; against
+    the faithful traversal the distance is equal on every ray and the index differs only where the winners tie.
+    (Measured: 0.7 - 4 % of such rays tie; rays from a continuous distribution do so about once per 10^6 at 1 M triangles.)"""
     d, s, o = full(case)
     tri = _mesh_triangles(d)
     rng = np.random.RandomState(5)
@@ -142,13 +143,19 @@ def test_rays_through_shared_vertices_tie_in_t(full, case):
     dirs = tri[rng.randint(0, len(tri), n), rng.randint(0, 3, n)] - org
     dirs = (dirs / np.linalg.norm(dirs, axis=1, keepdims=True)).astype(np.float32)
     pg, tg, ng = s.trace_rays(org, dirs, normals=True)
+    pr, tr, nr = s.trace_rays(org, dirs, normals=True, render_query=True)
+    pb, tb, nb = o.trace_rays(org, dirs, brute_force=True)
     po, to, no = o.trace_rays(org, dirs, traversal=0)
-    pr, tr, _ = s.trace_rays(org, dirs, normals=True, render_query=True)
-    hit = po >= 0
-    print("%s: %d of %d vertex rays hit, index agreement %.4f, distances equal on %.6f" % (case, hit.sum(), n, (pg == po).mean(), (tg[hit] == to[hit]).mean()))
-    assert np.array_equal(pg >= 0, hit) and np.array_equal(tg, to), "the nearest DISTANCE does not depend on the candidate order"
-    assert (pg == po).mean() >= 0.98
-    assert np.array_equal(tr, tg) and (pr == pg).mean() >= 0.98            # the render kernels' query: same distances
+    p2, t2, n2 = o.trace_rays(org, dirs, traversal=2)
+    hit = pb >= 0
+    print("%s: %d of %d vertex rays hit; index agreement with the reference's tie order %.4f, with the lowest-id order %.4f" % (
+        case, hit.sum(), n, (pg == po).mean(), (pg == pb).mean()))
+    assert np.array_equal(pb, p2) and np.array_equal(tb, t2), "oracle: traversal 2 is the brute-force order"
+    assert np.array_equal(pg, pb) and np.array_equal(tg, tb) and np.array_equal(ng[hit], nb[hit])
+    assert np.array_equal(pr, pb) and np.array_equal(tr, tb) and np.array_equal(nr[hit], nb[hit])
+    assert np.array_equal(to, tb), "the nearest DISTANCE does not depend on the tie rule"
+    differ = po != pb
+    assert differ.mean() <= 0.08 and differ.sum() > 0, "this test is about ties: some must occur"
 
 
 @pytest.mark.parametrize("case", list(CASES))
@@ -183,15 +190,21 @@ def test_replay_crops_match_oracle_full_size(full, lr, case):
         x, y, cov = _window(mesh, 128, target)
         crop = (x, y, 128, 128)
         img, sq, st = s.render(spp=spp, seed=11, splits=1, sumsq=True, crop=crop)
-        ref_sum, ref_sq, ost = o.render(make_params(lr, d.config, spp=spp, seed=11, crop=crop), traversal=0, rng_mode=0, math_mode=1)
+        # traversal 2: the reference's algorithm with the device's tie rule (lowest primitive id among equal distances):
+        # the path geometry must replay EXACTLY.  traversal 0: the reference's own tie order — a path diverges only where a
+        # ray ties (one sample in this 1 M-triangle crop, none at 144 k)
+        ref_sum, ref_sq, ost = o.render(make_params(lr, d.config, spp=spp, seed=11, crop=crop), traversal=2, rng_mode=0, math_mode=1)
+        fa_sum, _, fst = o.render(make_params(lr, d.config, spp=spp, seed=11, crop=crop), traversal=0, rng_mode=0, math_mode=1)
         ref = ref_sum / spp
         finite = np.isfinite(ref).all(-1) & np.isfinite(img).all(-1)
         frac = np.isclose(img, ref, rtol=1e-4, atol=1e-5).all(-1)[finite].mean()
-        print("%s %s crop %s (mesh coverage %.2f): replay agreement %.5f, rays gpu %d oracle %d, non-finite %d / %d" % (
-            case, what, crop, cov, frac, st["rays"], ost["rays"], st["nonfinite_samples"], ost["nonfinite_samples"]))
+        frac_fa = np.isclose(img, fa_sum / spp, rtol=1e-4, atol=1e-5).all(-1)[finite].mean()
+        print("%s %s crop %s (mesh coverage %.2f): replay agreement %.5f (reference tie order: %.5f), rays gpu %d oracle %d (reference tie order: %d), "
+              "non-finite %d / %d" % (case, what, crop, cov, frac, frac_fa, st["rays"], ost["rays"], fst["rays"], st["nonfinite_samples"], ost["nonfinite_samples"]))
         assert st["rays"] == ost["rays"], "path geometry must replay exactly"
         assert st["nonfinite_samples"] == ost["nonfinite_samples"]
-        assert frac >= 0.999
+        assert frac >= 0.999 and frac_fa >= 0.999
+        assert abs(st["rays"] - fst["rays"]) <= 1e-4 * fst["rays"]
         if what == "silhouette":
             assert 0.25 < cov < 0.75
 

@@ -215,6 +215,7 @@ def run_configs(lr, torch, l2_peak, hbm_peak):
         t0 = time.perf_counter()
         d = lr.Description(os.path.join(ROOT, "scenes", name + ".toml"), asset_root=roots[tris], resolution=(w, h))
         load_s = time.perf_counter() - t0
+        host_build_s = float(d.config.bvh_build_seconds)
         s = d.scene()
         accum = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
         s.render_accumulate(accum.data_ptr(), None, stream=stream, spp=min(spp, 4), seed=1)      # warm-up
@@ -236,6 +237,33 @@ def run_configs(lr, torch, l2_peak, hbm_peak):
         rays_per_s = st["rays"] / sec
         cpu_ms, cpu_mr, ost, sample, cores = oracle_sample(d, lambda spp: params_from_config(d.config, spp=spp, seed=1), min(spp, CPU_SAMPLE_SPP),
                                                           target_seconds=4.0, size=(w, h))
+        device_bvh = None
+        if tris > 0:
+            # the same scene with the BVH built on the device (bvh_build_gpu.cu): build time and what the tree costs the render
+            host_nodes, host_depth = int(d.desc.contents.n_nodes), int(d.desc.contents.bvh_depth)
+            d.rebuild_bvh("device")                              # first call: loads the kernels, grows the memory pool
+            wall = d.rebuild_bvh("device")
+            s_dev = d.scene()
+            s_dev.render_accumulate(accum.data_ptr(), None, stream=stream, spp=min(spp, 4), seed=1)
+            torch.cuda.synchronize()
+            s_dev.stats(stream)
+            dms = []
+            for rep in range(2):
+                flush.fill_(rep)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                s_dev.render_accumulate(accum.data_ptr(), None, stream=stream, spp=spp, seed=10 + rep)
+                b.record()
+                torch.cuda.synchronize()
+                dms.append(a.elapsed_time(b))
+            dst = s_dev.stats(stream)
+            device_bvh = {"build_ms_wall": 1e3 * wall, "build_ms_kernels": float(d.config.bvh_device_kernel_ms),
+                          "nodes": int(d.desc.contents.n_nodes), "depth": int(d.desc.contents.bvh_depth),
+                          "host_sah": {"build_s": host_build_s, "nodes": host_nodes, "depth": host_depth},
+                          "msamples_per_s": dst["samples"] / (sum(dms) * 1e-3) / 1e6, "ms_per_render": sum(dms) / len(dms),
+                          "what": "Morton-order radix tree (LBVH) built by CUDA kernels from the host triangle array to the host node array "
+                                  "(H2D + kernels + D2H); same images bit for bit, a slower tree than the host's binned SAH"}
+            s_dev.close()
         out.append({
             "config": label, "scene": "scenes/%s.toml" % name, "resolution": [w, h], "spp": spp,
             "integrator": "pt" if d.config.integrator == 0 else "pt-direct", "n_prims": int(d.config.n_prims),
@@ -246,7 +274,8 @@ def run_configs(lr, torch, l2_peak, hbm_peak):
             "l2_frac": (bm["bytes_per_ray"] * rays_per_s / 1e9 / l2_peak) if l2_peak else None,
             "l2_frac_tree_only": (bm["tree_bytes_per_ray"] * rays_per_s / 1e9 / l2_peak) if l2_peak else None,
             "hbm_frac": bm["bytes_per_ray"] * rays_per_s / 1e9 / hbm_peak,
-            "host_seconds": {"scene_load_s": load_s, "bvh_build_s": float(d.config.bvh_build_seconds)},
+            "host_seconds": {"scene_load_s": load_s, "bvh_build_s": host_build_s},
+            "device_bvh": device_bvh,
             "cpu": {"msamples_per_s": cpu_ms, "mrays_per_s": cpu_mr, "cores": cores, "kind": "port", "sample": sample,
                     "oracle_bvh_build_s": ost["build_seconds"]},
             "gpu_over_cpu": st["samples"] / sec / 1e6 / cpu_ms,

@@ -271,10 +271,8 @@ int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, 
     for (int k = 0; k < 3; k++) extent = std::fmax(extent, std::fmax(std::fabs(scene.lo[k]), std::fabs(scene.hi[k])));
     extent = std::fmax(extent, std::fmin(origin_extent, 1e30f));
     float kernel_ms = 0.0f, sec = 0.0f;
-    std::vector<LrTriangle> work(tris);
-    if (int rc = build_bvh_device(work, n, 4e-6f * extent + 1e-30f, kLeafTarget, nodes_out, depth_out, sec, kernel_ms)) return rc;
+    if (int rc = build_bvh_device(tris, n, 4e-6f * extent + 1e-30f, kLeafTarget, Builder::kStackGuardDepth, nodes_out, depth_out, sec, kernel_ms)) return rc;
     if (depth_out < Builder::kStackGuardDepth) {
-      tris.swap(work);
       if (builder_used) *builder_used = LR_BVH_DEVICE;
       if (device_kernel_ms) *device_kernel_ms = kernel_ms;
       seconds_out = std::chrono::duration<float>(std::chrono::steady_clock::now() - t0).count();
@@ -340,6 +338,7 @@ int validate_desc(const LrSceneDesc& d) {
   if ((d.n_materials > 0 && !d.materials) || (d.n_triangles > 0 && !d.triangles) || (d.n_spheres > 0 && !d.spheres) || (d.n_nodes > 0 && !d.nodes))
     return fail(LR_ERR_INVALID, "null array with non-zero count");
   if (d.n_flat_triangles < 0 || d.n_flat_triangles > d.n_triangles) return fail(LR_ERR_INVALID, "n_flat_triangles out of range");
+  if (d.n_flat_triangles > 32) return fail(LR_ERR_UNSUPPORTED, "more than 32 triangles outside the BVH (the kernels keep a lane's flat-list candidates in a 32-bit mask and the list in 2.5 KB of shared memory)");
   const int n_bvh_tris = d.n_triangles - d.n_flat_triangles;
   if ((n_bvh_tris > 0) != (d.n_nodes > 0)) return fail(LR_ERR_INVALID, "BVH nodes must be present iff triangles are in the BVH (use lr_host_scene_from_arrays)");
 

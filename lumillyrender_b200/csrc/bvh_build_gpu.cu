@@ -320,14 +320,16 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(int n, const int2* __res
   nodes_out[me] = out;
 }
 
+// scratch from the stream-ordered allocator (the device's default pool keeps freed blocks, lr_init: a second build reuses
+// them in microseconds where cudaMalloc / cudaFree cost milliseconds each and synchronise the device)
 struct DeviceBuffers {
   std::vector<void*> ptrs;
   template <class T> cudaError_t alloc(T** p, size_t count) {
-    cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
+    cudaError_t e = cudaMallocAsync((void**)p, std::max<size_t>(count, 1) * sizeof(T), 0);
     if (e == cudaSuccess) ptrs.push_back(*p);
     return e;
   }
-  ~DeviceBuffers() { for (void* p : ptrs) cudaFree(p); }
+  ~DeviceBuffers() { for (void* p : ptrs) cudaFreeAsync(p, 0); }
 };
 
 }  // namespace
@@ -335,8 +337,9 @@ struct DeviceBuffers {
 // Builds the tree over tris[0, n_tree) (the flat tail behind it is left alone) on the current device; on success `tris` is
 // permuted into leaf order and nodes_out holds the flattened tree.  leaf_target in 1..8.  seconds_out covers everything
 // from the host triangles to the host node array (H2D, kernels, D2H).
-int build_bvh_device(std::vector<LrTriangle>& tris, int n_tree, float pad, int leaf_target, std::vector<LrBvhNode>& nodes_out, int& depth_out,
-                     float& seconds_out, float& kernel_ms_out) {
+// If the tree comes out deeper than max_depth, `tris` and nodes_out are left untouched (depth_out says why).
+int build_bvh_device(std::vector<LrTriangle>& tris, int n_tree, float pad, int leaf_target, int max_depth, std::vector<LrBvhNode>& nodes_out,
+                     int& depth_out, float& seconds_out, float& kernel_ms_out) {
   const auto t0 = std::chrono::steady_clock::now();
   const int n = n_tree;
   if (n < 3) return fail(LR_ERR_INVALID, "build_bvh_device needs at least 3 triangles");
@@ -400,7 +403,9 @@ int build_bvh_device(std::vector<LrTriangle>& tris, int n_tree, float pad, int l
     if (e == cudaSuccess) e = cudaEventRecord(ev1, 0);
     NodeInfo root{};
     if (e == cudaSuccess) e = cudaMemcpy(&root, d_info, sizeof(root), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) {
+    if (e == cudaSuccess) e = cudaMemcpy(&depth_out, d_depth, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&kernel_ms_out, ev0, ev1);
+    if (e == cudaSuccess && depth_out < max_depth) {
       n_emitted = root.emits;
       if (root.tris != n || n_emitted < 1 || n_emitted > n - 1) {
         if (ev0) cudaEventDestroy(ev0);
@@ -409,10 +414,8 @@ int build_bvh_device(std::vector<LrTriangle>& tris, int n_tree, float pad, int l
       }
       nodes_out.resize(n_emitted);
       e = cudaMemcpy(nodes_out.data(), d_nodes, (size_t)n_emitted * sizeof(LrBvhNode), cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpy(tris.data(), d_out, (size_t)n * sizeof(LrTriangle), cudaMemcpyDeviceToHost);
     }
-    if (e == cudaSuccess) e = cudaMemcpy(tris.data(), d_out, (size_t)n * sizeof(LrTriangle), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaMemcpy(&depth_out, d_depth, sizeof(int), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaEventElapsedTime(&kernel_ms_out, ev0, ev1);
   }
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);

@@ -211,6 +211,54 @@ LR_DEV bool tri_gate(const DevScene& sc, F3 o, F3 inv, int id) {
 //     lane with the most candidates needs, not as long as the list;
 //   * consecutive flat triangles with the same box (the two halves of a wall quad) share one gate test: tri_box[2i].w is 1
 //     where triangle i's box equals its predecessor's (set at upload, api.cpp).
+// Where the flat list is read from: boxes (2 x float4 per flat triangle, tri_box layout) and triangles (3 x float4, tris
+// layout), indexed by the position k in the flat list.  The probes read the scene arrays in global memory; the render
+// kernels stage both tables into shared memory once per CTA with one TMA bulk copy each (stage_flat_list below).
+struct FlatList { const float4* box; const float4* tri; };
+LR_DEV FlatList flat_list_global(const DevScene& sc) {
+  FlatList f;
+  f.box = sc.tri_box + 2 * (size_t)sc.n_bvh_tris;
+  f.tri = sc.tris + 3 * (size_t)sc.n_bvh_tris;
+  return f;
+}
+constexpr int kFlatListMax = 32;                                   // validate_desc (bvh_build.cpp) refuses longer lists
+constexpr int kFlatListFloat4 = kFlatListMax * 5;                  // 2 box + 3 triangle float4 per entry: 2560 B
+
+// Stages the flat list (the handful of wall / floor / light triangles EVERY ray gates and tests, path_vertex.inc) into the
+// CTA's shared memory with the bulk-copy engine: one thread arms an mbarrier with the byte count and issues two
+// cp.async.bulk copies (global -> shared, completion counted on the mbarrier: SASS UBLKCP + SYNCS), every thread then
+// waits on the barrier's phase.  Called once at kernel start by all threads of the CTA; `tab` holds kFlatListFloat4 float4.
+LR_DEV FlatList stage_flat_list(const DevScene& sc, float4* tab, unsigned long long* bar) {
+  const int nf = sc.n_tris - sc.n_bvh_tris;
+  FlatList f;
+  f.box = tab;
+  f.tri = tab + 2 * nf;
+  if (nf <= 0) return f;
+  const unsigned bar_s = (unsigned)__cvta_generic_to_shared(bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned box_bytes = (unsigned)nf * 32u, tri_bytes = (unsigned)nf * 48u;
+    const unsigned dst_box = (unsigned)__cvta_generic_to_shared(tab), dst_tri = (unsigned)__cvta_generic_to_shared(tab + 2 * nf);
+    const float4* src_box = sc.tri_box + 2 * (size_t)sc.n_bvh_tris;
+    const float4* src_tri = sc.tris + 3 * (size_t)sc.n_bvh_tris;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(box_bytes + tri_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_box), "l"(src_box), "r"(box_bytes), "r"(bar_s) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_tri), "l"(src_tri), "r"(tri_bytes), "r"(bar_s) : "memory");
+  }
+  unsigned done = 0;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(bar_s), "r"(0u) : "memory");
+  } while (!done);
+  return f;
+}
+
 LR_DEV constexpr bool cand_loop_enabled() {
 #ifdef LR_FLAT_ALL
   return false;
@@ -219,7 +267,7 @@ LR_DEV constexpr bool cand_loop_enabled() {
 #endif
 }
 template <bool COUNT>
-LR_DEV void flat_hits(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, int& best, TraceCounters& tc) {
+LR_DEV void flat_hits(const DevScene& sc, const FlatList fl, F3 o, F3 d, F3 inv, float& best_t, int& best, TraceCounters& tc) {
   for (int i = 0; i < sc.n_spheres; i++) {
     const float4 s = ldg4(sc.spheres + i);
     if (COUNT) tc.spheres++;
@@ -238,10 +286,10 @@ LR_DEV void flat_hits(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, int
   cand = n_flat >= 32 ? ~0u : (1u << n_flat) - 1u;
 #pragma unroll 1
   while (cand != 0u) {
-    const int i = sc.n_bvh_tris + __ffs(cand) - 1;
+    const int k = __ffs(cand) - 1, i = sc.n_bvh_tris + k;
     cand &= cand - 1u;
-    const float4* tp = sc.tris + 3 * (size_t)i;
-    const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
+    const float4* tp = fl.tri + 3 * k;
+    const float4 v0 = tp[0], v1 = tp[1], v2 = tp[2];
     if (COUNT) { tc.tris++; tc.flat_tris++; }
     const float t = triangle_mt(f3(v0), f3(v1), f3(v2), o, d);
     if (t >= 0.0f && LR_NEARER(sc, t, __float_as_int(v0.w), best_t, best) && tri_gate(sc, o, inv, i)) { best_t = t; best = i; }
@@ -249,8 +297,7 @@ LR_DEV void flat_hits(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, int
 #endif
 #pragma unroll 1
   for (int k = 0; k < (cand_loop_enabled() ? n_flat : 0); k++) {
-    const float4* bp = sc.tri_box + 2 * (size_t)(sc.n_bvh_tris + k);
-    const float4 lo = ldg4(bp + 0), hi = ldg4(bp + 1);
+    const float4 lo = fl.box[2 * k], hi = fl.box[2 * k + 1];
     if (lo.w == 0.0f) {                                            // warp-uniform: a new box
       pass = ref_slab_pass_select(f3(lo), f3(hi), o, inv);
       if (COUNT) tc.flat_boxes++;
@@ -259,13 +306,13 @@ LR_DEV void flat_hits(const DevScene& sc, F3 o, F3 d, F3 inv, float& best_t, int
   }
 #pragma unroll 1
   while (cand != 0u) {
-    const int i = sc.n_bvh_tris + __ffs(cand) - 1;
+    const int k = __ffs(cand) - 1;
     cand &= cand - 1u;
-    const float4* tp = sc.tris + 3 * (size_t)i;
-    const float4 v0 = ldg4(tp + 0), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
+    const float4* tp = fl.tri + 3 * k;
+    const float4 v0 = tp[0], v1 = tp[1], v2 = tp[2];
     if (COUNT) { tc.tris++; tc.flat_tris++; }
     const float t = triangle_mt(f3(v0), f3(v1), f3(v2), o, d);
-    if (t >= 0.0f && LR_NEARER(sc, t, __float_as_int(v0.w), best_t, best)) { best_t = t; best = i; }
+    if (t >= 0.0f && LR_NEARER(sc, t, __float_as_int(v0.w), best_t, best)) { best_t = t; best = sc.n_bvh_tris + k; }
   }
 }
 
@@ -444,7 +491,7 @@ LR_DEV void trace(const DevScene& sc, F3 o, F3 d, float& t_out, int& id_out, Tra
   const F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
   float best_t = 3.0e38f;
   int best = -1;
-  flat_hits<COUNT>(sc, o, d, inv, best_t, best, tc);
+  flat_hits<COUNT>(sc, flat_list_global(sc), o, d, inv, best_t, best, tc);
   if (sc.n_nodes > 0) bvh_traverse<COUNT>(sc, o, d, inv, best_t, best, tc);
   t_out = best_t;
   id_out = best;

@@ -60,8 +60,8 @@ void camera_pinhole(Vec3 position, Vec3 aperture_position, const float* sensor_s
 // radix tree comes out deeper than the device traversal stack)
 int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, int& depth_out, float& seconds_out, int& n_flat_out,
               float origin_extent = 0.0f, int builder = 0, int* builder_used = nullptr, float* device_kernel_ms = nullptr);
-int build_bvh_device(std::vector<LrTriangle>& tris, int n_tree, float pad, int leaf_target, std::vector<LrBvhNode>& nodes_out, int& depth_out,
-                     float& seconds_out, float& kernel_ms_out);
+int build_bvh_device(std::vector<LrTriangle>& tris, int n_tree, float pad, int leaf_target, int max_depth, std::vector<LrBvhNode>& nodes_out,
+                     int& depth_out, float& seconds_out, float& kernel_ms_out);
 
 int load_hdr_file(const std::string& path, std::vector<float>& rgb, int& w, int& h);
 

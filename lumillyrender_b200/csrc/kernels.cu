@@ -77,7 +77,7 @@ rays_kernel(const __grid_constant__ DevScene sc, long long n, const float* __res
     const F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     t = 3.0e38f;
     id = -1;
-    flat_hits<false>(sc, o, d, inv, t, id, tc);
+    flat_hits<false>(sc, flat_list_global(sc), o, d, inv, t, id, tc);
     if (sc.n_nodes > 0 && bvh_bounds_hit(sc, o, inv, t < 3.0e38f ? t * 1.0001f + 1e-4f : 3.0e38f)) {
       bvh_traverse_unified<false>(sc, o, d, inv, t, id, tc);
       if (id >= 0 && id < sc.n_bvh_tris && !bvh_hit_is_gated(sc, o, inv, id)) trace<false>(sc, o, d, t, id, tc);

@@ -116,6 +116,14 @@ render_pool_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ 
   constexpr int NR = INTEGRATOR == LR_INTEGRATOR_PT_DIRECT ? 2 : 1;     // rays a vertex can issue: extension (+ shadow)
   constexpr int NS = slots<INTEGRATOR>();
   constexpr int kWords = mask_words<INTEGRATOR>();
+  // the flat list every ray gates and tests, staged into shared memory by the bulk-copy engine (device_path.cuh)
+#ifndef LR_NO_STAGE_FLAT
+  __shared__ __align__(16) float4 flat_tab[kFlatListFloat4];
+  __shared__ __align__(8) unsigned long long flat_bar;
+  const FlatList flat = stage_flat_list(sc, flat_tab, &flat_bar);
+#else
+  const FlatList flat = flat_list_global(sc);
+#endif
   extern __shared__ float pool_smem[];
   const int lane = (int)(threadIdx.x & 31);
   const unsigned int n_units = (unsigned int)p.tiles_x * p.tiles_y * 32u * (unsigned int)p.splits;

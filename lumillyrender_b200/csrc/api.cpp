@@ -406,27 +406,6 @@ int lr_render_accumulate_device(const LrScene* s, const LrRenderParams* p, float
       ksq = s->d_partial_sq;
     }
   }
-  // LR_L2_PERSIST=1 (measurement knob): an L2 access-policy window over the BVH nodes + triangles (adjacent in the scene
-  // block) for this launch — persisting hits, streaming misses — for scenes whose arrays outgrow the 126 MB L2
-  bool l2_window = false;
-  if (std::getenv("LR_L2_PERSIST") != nullptr && s->dev.n_nodes > 0) {
-    int max_window = 0, max_persist = 0;
-    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, s->device);
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, s->device);
-    const char* base = (const char*)s->dev.nodes;
-    const size_t span = (size_t)((const char*)(s->dev.tris + 3 * (size_t)s->dev.n_tris) - base);
-    if (max_window > 0 && max_persist > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess) {
-      cudaStreamAttrValue attr;
-      std::memset(&attr, 0, sizeof(attr));
-      attr.accessPolicyWindow.base_ptr = (void*)base;
-      attr.accessPolicyWindow.num_bytes = std::min(span, (size_t)max_window);
-      attr.accessPolicyWindow.hitRatio = std::min(1.0f, 0.9f * (float)max_persist / (float)attr.accessPolicyWindow.num_bytes);
-      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-      l2_window = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
-      if (!l2_window) cudaGetLastError();
-    } else cudaGetLastError();
-  }
   LR_CUDA(cudaEventRecord(s->ev0, st));
   {
     // the unit cursor lives in the last word of the counter block (reset on the stream before every launch)
@@ -442,11 +421,6 @@ int lr_render_accumulate_device(const LrScene* s, const LrRenderParams* p, float
     if (d_sumsq) { LR_CUDA(launch_reduce_splits(d_sumsq, s->d_partial_sq, n, dp.splits, st)); s->acc_launches++; }
   }
   LR_CUDA(cudaEventRecord(s->ev1, st));
-  if (l2_window) {                                             // the caller's stream gets its default policy back
-    cudaStreamAttrValue attr;
-    std::memset(&attr, 0, sizeof(attr));
-    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
-  }
   s->ev_pending = true;
   s->acc_samples += (uint64_t)dp.crop_w * dp.crop_h * (uint64_t)dp.spp_count;
   s->last_splits = dp.splits;

@@ -252,7 +252,12 @@ int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, 
         std::sort(flat.begin(), flat.end());
       }
     }
-    if (!flat.empty()) {
+    // (a rebuild finds the flat triangles already at the tail, in order: nothing to move)
+    bool in_place = !flat.empty();
+    for (size_t i = 0; i < flat.size() && in_place; i++) in_place = flat[i] == n_all - (int)flat.size() + (int)i;
+    if (in_place) {
+      n_flat_out = (int)flat.size();
+    } else if (!flat.empty()) {
       std::vector<char> is_flat(n_all, 0);
       for (int i : flat) is_flat[i] = 1;
       std::vector<LrTriangle> re; re.reserve(n_all);

@@ -259,13 +259,6 @@ LR_DEV FlatList stage_flat_list(const DevScene& sc, float4* tab, unsigned long l
   return f;
 }
 
-LR_DEV constexpr bool cand_loop_enabled() {
-#ifdef LR_FLAT_ALL
-  return false;
-#else
-  return true;
-#endif
-}
 template <bool COUNT>
 LR_DEV void flat_hits(const DevScene& sc, const FlatList fl, F3 o, F3 d, F3 inv, float& best_t, int& best, TraceCounters& tc) {
   for (int i = 0; i < sc.n_spheres; i++) {
@@ -281,22 +274,8 @@ LR_DEV void flat_hits(const DevScene& sc, const FlatList fl, F3 o, F3 d, F3 inv,
   const int n_flat = sc.n_tris - sc.n_bvh_tris;                    // <= 24 (bvh_build.cpp: kFlatMax)
   unsigned cand = 0u;
   bool pass = false;
-#ifdef LR_FLAT_ALL
-  // A/B build (tools/ab.py): the primitive test on every flat triangle, the gate on those that would become the nearest hit
-  cand = n_flat >= 32 ? ~0u : (1u << n_flat) - 1u;
 #pragma unroll 1
-  while (cand != 0u) {
-    const int k = __ffs(cand) - 1, i = sc.n_bvh_tris + k;
-    cand &= cand - 1u;
-    const float4* tp = fl.tri + 3 * k;
-    const float4 v0 = tp[0], v1 = tp[1], v2 = tp[2];
-    if (COUNT) { tc.tris++; tc.flat_tris++; }
-    const float t = triangle_mt(f3(v0), f3(v1), f3(v2), o, d);
-    if (t >= 0.0f && LR_NEARER(sc, t, __float_as_int(v0.w), best_t, best) && tri_gate(sc, o, inv, i)) { best_t = t; best = i; }
-  }
-#endif
-#pragma unroll 1
-  for (int k = 0; k < (cand_loop_enabled() ? n_flat : 0); k++) {
+  for (int k = 0; k < n_flat; k++) {
     const float4 lo = fl.box[2 * k], hi = fl.box[2 * k + 1];
     if (lo.w == 0.0f) {                                            // warp-uniform: a new box
       pass = ref_slab_pass_select(f3(lo), f3(hi), o, inv);

@@ -90,13 +90,9 @@ render_persistent_kernel(const __grid_constant__ DevScene sc, const __grid_const
   const unsigned int n_units = (unsigned int)p.tiles_x * p.tiles_y * 32u * (unsigned int)p.splits;
   const bool want_sumsq = out_sumsq != nullptr;
   // the flat list every ray gates and tests, staged into shared memory by the bulk-copy engine (device_path.cuh)
-#ifndef LR_NO_STAGE_FLAT
   __shared__ __align__(16) float4 flat_tab[kFlatListFloat4];
   __shared__ __align__(8) unsigned long long flat_bar;
   const FlatList flat = stage_flat_list(sc, flat_tab, &flat_bar);
-#else
-  const FlatList flat = flat_list_global(sc);
-#endif
 
   F3 o = f3(0, 0, 0), T = f3(1, 1, 1), L = f3(0, 0, 0), sum = f3(0, 0, 0), sumsq = f3(0, 0, 0);
   // the rays in flight (same origin o): 0 = extension ray, 1 = shadow ray

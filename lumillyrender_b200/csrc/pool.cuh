@@ -68,7 +68,7 @@ __host__ __device__ constexpr int words_per_slot(bool want_sumsq) {
   return (INTEGRATOR == LR_INTEGRATOR_PT_DIRECT ? (int)W_PTD_COUNT : (int)W_PT_COUNT) + (want_sumsq ? 3 : 0);
 }
 template <int INTEGRATOR>
-__host__ __device__ constexpr int warp_words(bool want_sumsq) { return words_per_slot<INTEGRATOR>(want_sumsq) * slots<INTEGRATOR>() + 64; }   // + the selection list
+__host__ __device__ constexpr int warp_words(bool want_sumsq) { return words_per_slot<INTEGRATOR>(want_sumsq) * slots<INTEGRATOR>() + 32; }   // + the selection list
 
 // Takes the first `quota` set bits of the concatenation words[rot] | words[rot + 1] | ... (cyclic): their codes
 // word * 32 + bit go to list[0, n) in that order, the bits are cleared in `words`.  Returns n (warp-uniform).  Lane j
@@ -117,13 +117,9 @@ render_pool_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ 
   constexpr int NS = slots<INTEGRATOR>();
   constexpr int kWords = mask_words<INTEGRATOR>();
   // the flat list every ray gates and tests, staged into shared memory by the bulk-copy engine (device_path.cuh)
-#ifndef LR_NO_STAGE_FLAT
   __shared__ __align__(16) float4 flat_tab[kFlatListFloat4];
   __shared__ __align__(8) unsigned long long flat_bar;
   const FlatList flat = stage_flat_list(sc, flat_tab, &flat_bar);
-#else
-  const FlatList flat = flat_list_global(sc);
-#endif
   extern __shared__ float pool_smem[];
   const int lane = (int)(threadIdx.x & 31);
   const unsigned int n_units = (unsigned int)p.tiles_x * p.tiles_y * 32u * (unsigned int)p.splits;
@@ -258,60 +254,12 @@ render_pool_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ 
       // ================================================================ phase B
       // a batch of up to 32 pending rays (extension or shadow) traverses the BVH: one loop that advances every lane by
       // at most one inner node and one triangle test per iteration (trav_step), optimistic accept, the nearest hit gated
-      // once at the end, strict re-trace in the rare case the gate rejects it.  (Refilling idle lanes from the pool
-      // inside this loop was measured too: the bookkeeping costs more than the width it keeps, profiles/r01_e_*.)
-#ifdef LR_POOL_B2
-      // Two rays per lane: a lane that holds two independent traversals has two node fetches in flight and idles only
-      // when BOTH are done — the BVH phase is bound by the latency of its dependent fetches and by the tail of its longest
-      // ray (9.6 of 32 lanes active with one ray per lane, profiles/r01_e_render_kernel_regions.txt).
-      const int n_sel = select_take<NR * kWords>(list, lane, pend, 64, rot_b);
-      rot_b = rot_b + 1 == NR * kWords ? 0 : rot_b + 1;
-      {
-        TravState ts[2];
-        int stk0[kStackDepth], stk1[kStackDepth];
-        int slot_of[2];
-        bool shadow_of[2];
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-          const bool on = lane + 32 * k < n_sel;
-          const int item = on ? list[lane + 32 * k] : 0;
-          const int s = item % (32 * kWords);
-          const bool shadow = NR == 2 && item >= 32 * kWords;
-          slot_of[k] = on ? s : -1;
-          shadow_of[k] = shadow;
-          ts[k].cur = kTravDone; ts[k].leaf_left = 0;
-          if (on) {
-            const F3 o = f3(SLF(W_OX), SLF(W_OY), SLF(W_OZ));
-            const F3 d = shadow ? f3(SLF(W_D1X), SLF(W_D1Y), SLF(W_D1Z)) : f3(SLF(W_DX), SLF(W_DY), SLF(W_DZ));
-            const F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-            trav_begin(ts[k], k == 0 ? stk0 : stk1, o, d, inv, shadow ? SLF(W_T1) : SLF(W_T0), shadow ? SLI(W_ID1) : SLI(W_ID0));
-          }
-        }
-        while (!trav_done(ts[0]) || !trav_done(ts[1])) {
-          if (!trav_done(ts[0])) trav_step<COUNT>(sc, ts[0], stk0, tc);
-          if (!trav_done(ts[1])) trav_step<COUNT>(sc, ts[1], stk1, tc);
-        }
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-          const int s = slot_of[k];
-          if (s >= 0) {
-            float t = ts[k].best_t;
-            int id = ts[k].best;
-            if (id >= 0 && id < sc.n_bvh_tris && !bvh_hit_is_gated(sc, ts[k].o, ts[k].inv, id)) {
-              t = shadow_of[k] ? SLF(W_T1) : SLF(W_T0); id = shadow_of[k] ? SLI(W_ID1) : SLI(W_ID0);   // the flat candidate the ray came with
-              trace_strict<COUNT>(sc, ts[k].o, ts[k].d, &t, &id, &tc);
-              n_retrace++;
-            }
-            if (shadow_of[k]) { SLF(W_T1) = t; SLI(W_ID1) = id; } else { SLF(W_T0) = t; SLI(W_ID0) = id; }
-          }
-        }
-      }
-      if (false) {
-#else
+      // once at the end, strict re-trace in the rare case the gate rejects it.  (Measured and dropped, each bit-exact: idle
+      // lanes refilled from the pending rays inside this loop — r01 and again r02 with pools of 64 / 96 slots: 14-22 % slower;
+      // two rays per lane: 23 % slower; the tree collapsed to 4-wide nodes: 4 % slower.  profiles/r02_b_ab.txt, r02_c_ab.txt.)
       const int n_sel = select_take<NR * kWords>(list, lane, pend, 32, rot_b);
       rot_b = rot_b + 1 == NR * kWords ? 0 : rot_b + 1;
       if (lane < n_sel) {
-#endif
         const int item = list[lane];                          // mask word * 32 + bit; the shadow rays' words follow the kWords extension words
         const int s = item % (32 * kWords);
         const bool shadow = NR == 2 && item >= 32 * kWords;

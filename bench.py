@@ -427,9 +427,13 @@ def main():
             l2_peak = None
         dram = traffic.get("dram_bytes_per_launch")
         algorithmic = b_ray * rays_per_launch
+        # the ncu capture is one launch of `spp_of_capture` samples per pixel (ncu cannot replay the bench's 2 s launch): the
+        # algorithmic bytes of THAT launch are what its DRAM traffic is compared with
+        cap_spp = traffic.get("spp_of_capture") or (spp_total / world)
+        algorithmic_capture = algorithmic * cap_spp / (spp_total / world)
         # the scene is L2-resident when the kernel's measured DRAM traffic is a small fraction of the bytes the traversal
-        # asks for: the bound is then L2 (tree fetches) / L1 (flat-list broadcast), not HBM
-        l2_resident = dram is not None and dram < 0.1 * algorithmic
+        # asks for: the bound is then L2 (tree fetches) / L1 + shared memory (flat list), not HBM
+        l2_resident = dram is not None and dram < 0.1 * algorithmic_capture
         measured_l2 = None
         if traffic.get("lts_bytes_per_launch") and traffic.get("kernel_ms_of_capture"):
             measured_l2 = traffic["lts_bytes_per_launch"] / (traffic["kernel_ms_of_capture"] * 1e-3) / 1e9
@@ -441,7 +445,9 @@ def main():
                    "measured_l2_gbs": measured_l2, "measured_l2_frac": (measured_l2 / l2_peak) if (measured_l2 and l2_peak) else None,
                    "measured_l2_source": traffic.get("source"),
                    "kernel": kernel_name(d) + " (pool.cuh)", "kernel_ms_per_launch": launch_ms, "rays_per_launch": rays_per_launch,
-                   "algorithmic_bytes_per_launch": algorithmic}
+                   "algorithmic_bytes_per_launch": algorithmic,
+                   "traffic_note": "traffic = dram__bytes_read + dram__bytes_write of ONE %s-spp launch of this kernel on this workload (profiles/traffic.json); "
+                                   "the same launch asks for %.3g algorithmic bytes" % (cap_spp, algorithmic_capture)}
         roof_l2.update(bm)
         roof_hbm = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": dram,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of %s)" % which,

@@ -39,7 +39,9 @@ def cell(n):
 
 eff = "—"
 if 8 in multi:
-    eff = "%.1f %% (e2e %.1f %%)" % (100.0 * multi[8]["value"] / (8 * n1["value"]), 100.0 * multi[8]["e2e"]["value"] / (8 * n1["e2e"]["value"]))
+    b = multi.get(1, n1)                                  # the N = 1 run of the same box, if given
+    eff = "%.1f %% (e2e %.1f %%)%s" % (100.0 * multi[8]["value"] / (8 * b["value"]), 100.0 * multi[8]["e2e"]["value"] / (8 * b["e2e"]["value"]),
+                                       " vs %.0f on the same box" % b["value"] if 1 in multi else "")
 rows.append("| 5 sample.toml, %dx%d, %d spp total (strong scaling) | %.2f · %.1f (%d) | **%.0f · %.0f** (e2e %.0f) | %s | %s | %s | %s | %.3f (tree only %.3f) | %.3f | 100 %% of 2.63 M px / 0 (bit-equal) / 99.95 %% / 1.14 (full size) |" % (
     n1["config"]["resolution"][0], n1["config"]["resolution"][1], n1["config"]["spp_total"], cb.get("value", float("nan")), cb.get("mrays_per_s", float("nan")),
     cb.get("cores", 0), n1["value"], n1["mrays_per_s"], n1["e2e"]["value"], cell(2), cell(4), cell(8), eff, r["frac"], r["frac_tree_only"], rh.get("frac", float("nan"))))

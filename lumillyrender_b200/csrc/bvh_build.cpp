@@ -214,6 +214,49 @@ struct Builder {
 
 }  // namespace
 
+// Outliers leave the tree.  A small primitive far from the rest — the area light of scenes/welcome-2018.toml hangs 2000 units
+// above the mesh — makes the tree's bounds span the scene, so that nearly every ray (and every shadow ray, which is AIMED at
+// the light) passes the reach test, visits the root and leaves again: one-step traversals that fill the BVH phase and idle
+// its lanes (ncu: 2.8 of 32 lanes in the node loop of welcome-2018).  Both builders put such an outlier where SAH / Morton
+// order puts it: in a leaf directly under the root.  While the root has a LEAF child whose removal at least halves the surface
+// area of the tree's bounds, and the flat list has room, the leaf's triangles join the flat list (which every ray gates with
+// one box test, device_path.cuh: flat_hits) and the other child becomes the root.  O(n) per peel; the nearest hit does not
+// depend on which list a triangle is in.
+static void peel_outliers(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes, int& depth, int& n_flat) {
+  auto box_area = [](const float* f) {
+    const float dx = f[3] - f[0], dy = f[4] - f[1], dz = f[5] - f[2];
+    return 2.0f * (dx * dy + dy * dz + dz * dx);
+  };
+  while (nodes.size() >= 2) {
+    const LrBvhNode root = nodes[0];
+    int leaf = -1;
+    for (int k = 0; k < 2; k++) if (root.c[k] < 0 && root.c[1 - k] >= 0) leaf = k;       // a leaf beside an inner node
+    if (leaf < 0) break;
+    const int code = ~root.c[leaf], first = code >> 3, count = (code & 7) + 1;
+    if (n_flat + count > kFlatMax) break;
+    if (root.c[1 - leaf] != 1) break;                         // not depth-first order (cannot happen with our builders): leave the tree alone
+    float uni[6];
+    for (int a = 0; a < 3; a++) { uni[a] = std::fmin(root.f[a], root.f[6 + a]); uni[3 + a] = std::fmax(root.f[3 + a], root.f[9 + a]); }
+    if (!(box_area(root.f + 6 * (1 - leaf)) <= 0.5f * box_area(uni))) break;
+    const int n_tree = (int)tris.size() - n_flat;
+    // the leaf's triangles go to the end of the tree range, i.e. to the front of the flat tail
+    std::rotate(tris.begin() + first, tris.begin() + first + count, tris.begin() + n_tree);
+    n_flat += count;
+    // the inner child (node 1 in depth-first order) becomes the root: drop node 0, shift indices and leaf ranges
+    nodes.erase(nodes.begin());
+    for (LrBvhNode& nd : nodes) {
+      for (int k = 0; k < 2; k++) {
+        if (nd.c[k] >= 0) nd.c[k] -= 1;
+        else {
+          const int c = ~nd.c[k], f0 = c >> 3, cnt = c & 7;
+          if (f0 > first) nd.c[k] = ~(((f0 - count) << 3) | cnt);
+        }
+      }
+    }
+    depth -= 1;
+  }
+}
+
 int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, int& depth_out, float& seconds_out, int& n_flat_out,
               float origin_extent, int builder, int* builder_used, float* device_kernel_ms) {
   if (builder_used) *builder_used = LR_BVH_HOST;
@@ -278,6 +321,7 @@ int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, 
     float kernel_ms = 0.0f, sec = 0.0f;
     if (int rc = build_bvh_device(tris, n, 4e-6f * extent + 1e-30f, kLeafTarget, Builder::kStackGuardDepth, nodes_out, depth_out, sec, kernel_ms)) return rc;
     if (depth_out < Builder::kStackGuardDepth) {
+      peel_outliers(tris, nodes_out, depth_out, n_flat_out);
       if (builder_used) *builder_used = LR_BVH_DEVICE;
       if (device_kernel_ms) *device_kernel_ms = kernel_ms;
       seconds_out = std::chrono::duration<float>(std::chrono::steady_clock::now() - t0).count();
@@ -333,6 +377,7 @@ int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, 
   tris.swap(permuted);
   nodes_out.swap(bld.nodes);
   depth_out = bld.max_depth;
+  peel_outliers(tris, nodes_out, depth_out, n_flat_out);
   seconds_out = std::chrono::duration<float>(std::chrono::steady_clock::now() - t0).count();
   return LR_OK;
 }

@@ -575,3 +575,77 @@ def test_device_bvh_builder_refuses_loudly_without_a_gpu(lr, assets):
     small = load_scene(lr, "new-cbox", (32, 32))
     small.rebuild_bvh("device")                       # flat-only scene: nothing to build, no device needed
     assert small.config.bvh_builder == 0
+
+
+def _check_tree(desc):
+    """Walks the flattened BVH of a description: every tree triangle lies in exactly one leaf, inside that leaf's box and
+    inside every ancestor's box (the device's node test is a cull: a box that does not contain its triangles loses hits)."""
+    n_tree = desc.n_triangles - desc.n_flat_triangles
+    seen = np.zeros(n_tree, dtype=np.int32)
+    if desc.n_nodes == 0:
+        assert n_tree == 0
+        return 0
+    tri = np.ctypeslib.as_array(C.cast(desc.triangles, C.POINTER(C.c_float)), shape=(desc.n_triangles, 11))[:, :9].reshape(-1, 3, 3)
+    stack = [(0, np.full(3, -np.inf), np.full(3, np.inf), 1)]
+    depth = 0
+    while stack:
+        i, plo, phi, dep = stack.pop()
+        depth = max(depth, dep)
+        nd = desc.nodes[i]
+        for k in range(2):
+            lo, hi = np.array(nd.f[6 * k:6 * k + 3]), np.array(nd.f[6 * k + 3:6 * k + 6])
+            c = nd.c[k]
+            if c >= 0:
+                stack.append((c, np.maximum(lo, plo), np.minimum(hi, phi), dep + 1))
+            else:
+                code = ~c
+                first, count = code >> 3, (code & 7) + 1
+                assert nd.n[k] == count and first + count <= n_tree
+                seen[first:first + count] += 1
+                t = tri[first:first + count].reshape(-1, 3)
+                assert (t >= np.maximum(lo, plo)).all() and (t <= np.minimum(hi, phi)).all()
+    assert (seen == 1).all() or (n_tree == 1 and (seen == 2).all())       # a single triangle is referenced by both root slots
+    return depth
+
+
+def test_outliers_are_peeled_from_the_tree_into_the_flat_list(lr):
+    """A small primitive far from a mesh (the area light of scenes/welcome-2018.toml) would make the tree's bounds span the
+    scene and send nearly every ray through the root for nothing: bvh_build.cpp moves a root-level leaf whose removal at
+    least halves the surface area of the tree's bounds into the flat list.  The tree that remains must still be a valid
+    tree over exactly the other triangles."""
+    from lumillyrender_b200 import capi
+    rng = np.random.RandomState(9)
+    n = 3000
+    T = (capi.LrTriangle * (n + 2))()
+    for i in range(n):
+        c = rng.uniform(0, 10, 3)
+        v = (c + rng.normal(0, 0.05, (3, 3))).astype(np.float32)
+        T[i].p0[:] = v[0]; T[i].p1[:] = v[1]; T[i].p2[:] = v[2]; T[i].material = 0; T[i].prim_id = i
+    far = np.array([[100, 300, -50], [101, 300, -50], [101, 300, -49], [100, 300, -49]], dtype=np.float32)
+    for k, (a, b, c) in enumerate(((0, 1, 2), (0, 2, 3))):
+        T[n + k].p0[:] = far[a]; T[n + k].p1[:] = far[b]; T[n + k].p2[:] = far[c]; T[n + k].material = 0; T[n + k].prim_id = n + k
+    mats = (capi.LrMaterial * 1)()
+    cam = capi.LrCamera()
+    m = (C.c_float * 16)()
+    lib = capi.load_library()
+    lib.lr_matrix_look_at((C.c_float * 3)(5, 5, 40), (C.c_float * 3)(5, 5, 5), (C.c_float * 3)(0, 1, 0), m)
+    lib.lr_camera_ideal_pinhole(m, 40.0, 8, 8, C.byref(cam))
+    d = lr.Description.from_arrays(mats, T, [], cam)
+    desc = d.desc.contents
+    flat_ids = sorted(desc.triangles[i].prim_id for i in range(desc.n_triangles - desc.n_flat_triangles, desc.n_triangles))
+    assert flat_ids == [n, n + 1], "the far quad (and nothing else: the mesh triangles are tiny) must be in the flat list"
+    assert sorted(desc.triangles[i].prim_id for i in range(desc.n_triangles)) == list(range(n + 2))
+    depth = _check_tree(desc)
+    assert depth <= desc.bvh_depth
+    root = desc.nodes[0]
+    assert max(root.f[3], root.f[9]) < 11 and max(root.f[4], root.f[10]) < 11, "the tree's bounds are the mesh's"
+
+
+@pytest.mark.parametrize("name", ["sample", "welcome-2018", "vr"])
+def test_scene_trees_contain_their_triangles(lr, assets, name):
+    d = load_scene(lr, name, (64, 64))
+    desc = d.desc.contents
+    assert _check_tree(desc) <= desc.bvh_depth
+    if name == "welcome-2018":
+        # the light quad hangs 2000 units above the mesh: peeled into the flat list (14 large triangles + 2)
+        assert desc.n_flat_triangles == 16

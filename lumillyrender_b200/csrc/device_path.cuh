@@ -757,8 +757,13 @@ LR_DEV unsigned long long f32_to_usize(float v) {   // Rust `as usize`: saturati
 LR_COLD F3 sky_ibl(const float4* __restrict__ pixels, int sky_height, float longitude_offset, F3 d) {
   const float theta = acosf(d.y);
   const float phi = atan2f(d.z, d.x);
-  const float u = fmodf((phi + kPI + longitude_offset) / (2.0f * kPI), 1.0f);
-  const float v = fmodf(theta / kPI, 1.0f);
+  // `x % 1.0` (sky.rs:60-61) is x - trunc(x) EXACTLY: below 2^23 the difference of x and its integer part needs no more
+  // bits than x has, above it x is an integer (the signed zero fmod would give there indexes the same texel), NaN and inf
+  // give NaN either way.  Two subtractions instead of two calls of the library's fmodf loop on every path that ends in the sky.
+  const float uq = (phi + kPI + longitude_offset) / (2.0f * kPI);
+  const float vq = theta / kPI;
+  const float u = uq - truncf(uq);
+  const float v = vq - truncf(vq);
   const unsigned long long height = (unsigned long long)sky_height;
   const unsigned long long width = height * 2ull;
   const unsigned long long all = width * height;

@@ -32,3 +32,22 @@ def test_fast_fmod_is_exact():
         assert bad.size == 0, (m, x[bad[:5]], got[bad[:5]], want[bad[:5]])
 
 
+
+
+def test_fmod_by_one_is_x_minus_trunc_exactly():
+    """sky.rs:60-61 takes `% 1.0` of the equirect coordinates; the device computes x - trunc(x) (device_path.cuh: sky_ibl).
+    Same IEEE operations in numpy: equal bit for bit to fmod on random, tiny, huge, negative and special inputs (up to the
+    sign of a zero result, which indexes the same texel)."""
+    rng = np.random.RandomState(3)
+    x = np.concatenate([
+        rng.uniform(-4, 4, 2_000_000), rng.uniform(-1e-3, 1e-3, 200_000), rng.uniform(-2e7, 2e7, 200_000),
+        np.ldexp(rng.uniform(0.5, 1, 200_000), rng.randint(-40, 40, 200_000)) * rng.choice([-1, 1], 200_000),
+        np.array([0.0, -0.0, 1.0, -1.0, 0.99999994, 1.0000001, 8388608.0, -8388608.0, 16777216.0, 3.4e38, np.inf, -np.inf, np.nan]),
+    ]).astype(np.float32)
+    with np.errstate(invalid="ignore"):
+        want = np.fmod(x, np.float32(1.0))
+        got = x - np.trunc(x)
+    assert got.dtype == np.float32
+    both_nan = np.isnan(want) & np.isnan(got)
+    assert np.array_equal(want[~both_nan], got[~both_nan])          # -0.0 == +0.0 here: the texel index floor(W * u) is 0 for both
+    assert both_nan.sum() == 3

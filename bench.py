@@ -192,7 +192,7 @@ def kernel_name(d):
     desc = d.desc.contents
     integ = "pt" if d.config.integrator == 0 else "pt-direct"
     tree = desc.n_nodes > 0
-    pool = tree and d.config.integrator == 0            # persistent_inst.cu: LR_USE_POOL
+    pool = tree                                         # persistent_inst.cu: LR_USE_POOL
     return "%s<%s, %s>" % ("render_pool_kernel" if pool else "render_persistent_kernel", integ, "tree" if tree else "flat")
 
 

@@ -85,7 +85,7 @@ def build_library(force=False, verbose=False, extra=(), obj_dir=None):
                     # vector / scalar quotients out of line: +4.6 % for the one-path-per-lane kernel over a BVH (it is
                     # instruction-fetch bound), -4.5 % for the pool kernel (pt over a BVH): profiles/r01_e_ab_s50.txt
                     defs.append("-DLR_DIV_OUT_OF_LINE")
-                if not ggx:
+                if not ggx or (tree and integ == 1 and os.environ.get("LR_BUILD_PTD_GGX_OUT")):
                     defs.append("-DLR_GGX_OUT_OF_LINE")
                 jobs.append(([_nvcc()] + flags + defs + ["-c", os.path.join(CSRC, "persistent_inst.cu"), "-o", o], verbose))
     with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:

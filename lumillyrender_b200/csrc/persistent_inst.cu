@@ -10,12 +10,15 @@
 #error "compile with -DLR_INST_INTEGRATOR=0|1 -DLR_INST_TREE=0|1 -DLR_INST_GGX=0|1"
 #endif
 
-// Which organisation runs a build by default (A/B on one box, profiles/r01_e_ab_*.txt): the pool kernel (pool.cuh) for
-// pure path tracing over a BVH (sample.toml: 49.0 -> 37.9 ms), the one-path-per-lane kernel (persistent.cuh) for the
-// flat-only scenes (no phase B to feed) and for pt-direct over a BVH, whose 42-word slots leave room for too few warps
-// (welcome-2018: 52.7 ms against 62.7 ms).  The units for scenes with a BVH hold BOTH organisations: DevParams.organisation
-// (LR_ORGANISATION=persistent|pool, api.cpp) overrides the default so that tests can compare their images bit for bit.
-#define LR_USE_POOL (LR_INST_TREE && LR_INST_INTEGRATOR == LR_INTEGRATOR_PT)
+// Which organisation runs a build by default (A/B on one box, profiles/r01_e_ab_*.txt, r02_e_sweep.txt): the pool kernel (pool.cuh)
+// for every scene with a BVH — pure path tracing (sample.toml: 49.0 -> 36.3 ms) and, since round 2, pt-direct too (welcome-2018:
+// 50.4 -> 45.8 ms once its slots were fetched lazily and the far light had left the tree, bvh_build.cpp: peel_outliers) — the
+// one-path-per-lane kernel (persistent.cuh) for the flat-only scenes (no phase B to feed).  The units for scenes with a BVH hold
+// BOTH organisations: DevParams.organisation (LR_ORGANISATION=persistent|pool, api.cpp) overrides the default so that tests can
+// compare their images bit for bit.
+#ifndef LR_USE_POOL
+#define LR_USE_POOL (LR_INST_TREE)
+#endif
 
 namespace lr {
 

@@ -59,7 +59,7 @@ enum {
 template <int INTEGRATOR>
 __host__ __device__ constexpr int slots() { return INTEGRATOR == LR_INTEGRATOR_PT_DIRECT ? LR_POOL_SLOTS_PTD : LR_POOL_SLOTS; }
 static_assert(LR_POOL_SLOTS % 16 == 0 && LR_POOL_SLOTS >= 48 && LR_POOL_SLOTS <= 128, "a warp's pool holds 48 .. 128 paths");
-static_assert(LR_POOL_SLOTS_PTD % 16 == 0 && LR_POOL_SLOTS_PTD >= 48 && LR_POOL_SLOTS_PTD <= 128, "a warp's pool holds 48 .. 128 paths");
+static_assert(LR_POOL_SLOTS_PTD % 8 == 0 && LR_POOL_SLOTS_PTD >= 40 && LR_POOL_SLOTS_PTD <= 128, "a warp's pool holds 40 .. 128 paths");
 template <int INTEGRATOR>
 __host__ __device__ constexpr int mask_words() { return (slots<INTEGRATOR>() + 31) / 32; }     // mask words per kind of work
 

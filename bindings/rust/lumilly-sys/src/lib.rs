@@ -38,6 +38,7 @@ use std::os::raw::{c_char, c_int, c_void};
 pub enum LrScene {}
 pub enum LrHostScene {}
 pub enum LrFilm {}
+pub enum LrMultiScene {}
 pub const LR_AOV_NORMAL: i32 = 0;
 pub const LR_AOV_DEPTH: i32 = 1;
 pub const LR_BVH_HOST: i32 = 0;
@@ -60,6 +61,10 @@ extern "C" {
     /// one peer-reading reduce kernel on devices[0])
     pub fn lr_render_multi(desc: *const LrSceneDesc, params: *const LrRenderParams, n_devices: i32, devices: *const i32,
                            out_rgb: *mut f32, out_sumsq: *mut f32, stats: *mut LrStats) -> c_int;
+    /// the multi-GPU scene as a handle: set-up once, then renders only
+    pub fn lr_multi_scene_create(desc: *const LrSceneDesc, n_devices: i32, devices: *const i32, out: *mut *mut LrMultiScene) -> c_int;
+    pub fn lr_multi_render(ms: *mut LrMultiScene, params: *const LrRenderParams, out_rgb: *mut f32, out_sumsq: *mut f32, stats: *mut LrStats) -> c_int;
+    pub fn lr_multi_scene_destroy(ms: *mut LrMultiScene);
     /// Scene::normal / Scene::depth (scene.rs:48-62) of the camera rays of the sample range, averaged per pixel
     pub fn lr_render_aov(scene: *const LrScene, params: *const LrRenderParams, kind: i32, out: *mut f32) -> c_int;
     /// progressive / resumable rendering (the hook main.rs:81-91 abandoned): per-pixel sums kept on the device

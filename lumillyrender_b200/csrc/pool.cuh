@@ -145,14 +145,6 @@ render_pool_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ 
   TraceCounters tc;
   tc.nodes = tc.tris = tc.spheres = tc.flat_tris = tc.flat_boxes = 0;
   int rot_a = 0, rot_b = 0;
-#ifdef LR_POOL_CLASSIFY
-  // A/B build: slots whose ray STARTS on a mesh triangle (a bounce off the mesh: it starts inside the tree's bounds and its
-  // traversal is long) are told from those whose ray comes from a wall or the camera; a BVH batch is formed from one class
-  // when that class alone has LR_POOL_CLASSIFY rays, so that the 32 rays of a batch are of similar length
-  unsigned cls[kWords];
-#pragma unroll
-  for (int i = 0; i < kWords; i++) cls[i] = 0u;
-#endif
 
   while (true) {
     unsigned rdy[kWords];
@@ -228,9 +220,6 @@ render_pool_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ 
     if (want_sumsq) { SLF(W_SQ) = sumsq.x; SLF(W_SQ + 1) = sumsq.y; SLF(W_SQ + 2) = sumsq.z; }                            \
   } while (0)
 
-#ifdef LR_POOL_CLASSIFY
-      const bool hit_on_mesh = ready && (flags & F_HAS_RAY) && id0 >= 0 && id0 < sc.n_bvh_tris;
-#endif
       // the vertex itself: the code of persistent.cuh's phase A, on the variables loaded above
 #include "path_vertex.inc"
 
@@ -260,10 +249,6 @@ render_pool_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ 
         pend[i] |= __reduce_or_sync(kFull, (go && pend0 && w == i) ? bit : 0u);
         if (NR == 2) pend[(NR - 1) * kWords + i] |= __reduce_or_sync(kFull, (go && pend1 && w == i) ? bit : 0u);
         dead[i] |= __reduce_or_sync(kFull, (ready && !alive && w == i) ? bit : 0u);
-#ifdef LR_POOL_CLASSIFY
-        cls[i] = (cls[i] & ~__reduce_or_sync(kFull, (ready && w == i) ? bit : 0u)) |
-                 __reduce_or_sync(kFull, (go && hit_on_mesh && !need_new && w == i) ? bit : 0u);
-#endif
       }
     } else {
       // ================================================================ phase B
@@ -271,31 +256,9 @@ render_pool_kernel(const __grid_constant__ DevScene sc, const __grid_constant__ 
       // at most one inner node and one triangle test per iteration (trav_step), optimistic accept, the nearest hit gated
       // once at the end, strict re-trace in the rare case the gate rejects it.  (Measured and dropped, each bit-exact: idle
       // lanes refilled from the pending rays inside this loop — r01 and again r02 with pools of 64 / 96 slots: 14-22 % slower;
-      // two rays per lane: 23 % slower; the tree collapsed to 4-wide nodes: 4 % slower.  profiles/r02_b_ab.txt, r02_c_ab.txt.)
-#ifdef LR_POOL_CLASSIFY
-      int n_sel;
-      {
-        int n1 = 0;
-#pragma unroll
-        for (int i = 0; i < NR * kWords; i++) n1 += __popc(pend[i] & cls[i % kWords]);
-        const int n0 = nB - n1;
-        const int pick = n1 >= LR_POOL_CLASSIFY && n1 >= n0 ? 1 : (n0 >= LR_POOL_CLASSIFY ? 0 : (n1 >= LR_POOL_CLASSIFY ? 1 : -1));
-        if (pick < 0) {
-          n_sel = select_take<NR * kWords>(list, lane, pend, 32, rot_b);
-        } else {
-          unsigned part[NR * kWords];
-#pragma unroll
-          for (int i = 0; i < NR * kWords; i++) part[i] = pend[i] & (pick ? cls[i % kWords] : ~cls[i % kWords]);
-#pragma unroll
-          for (int i = 0; i < NR * kWords; i++) pend[i] &= ~part[i];
-          n_sel = select_take<NR * kWords>(list, lane, part, 32, rot_b);
-#pragma unroll
-          for (int i = 0; i < NR * kWords; i++) pend[i] |= part[i];          // what the batch did not take stays pending
-        }
-      }
-#else
+      // two rays per lane: 23 % slower; the tree collapsed to 4-wide nodes: 4 % slower; batches formed from one class of rays —
+      // bounces off the mesh apart from rays that come from a wall or the camera: 2-6 % slower.  profiles/r02_{b,c,h}_ab.txt.)
       const int n_sel = select_take<NR * kWords>(list, lane, pend, 32, rot_b);
-#endif
       rot_b = rot_b + 1 == NR * kWords ? 0 : rot_b + 1;
       if (lane < n_sel) {
         const int item = list[lane];                          // mask word * 32 + bit; the shadow rays' words follow the kWords extension words

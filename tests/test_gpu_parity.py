@@ -150,6 +150,9 @@ def test_statistical_parity_independent_streams(scenes, lr, name, spp):
     frac, z, relmse = mc_agreement(img[ok], sq[ok], spp, ref_sum[ok] / spp, ref_sq[ok], spp)
     print("%s: within-3sigma %.4f, image-mean z %.2f, relMSE %.4g" % (name, frac, z, relmse))
     assert frac >= 0.99
+    # 4 standard errors here: at 16-32 spp the firefly scenes (sun-disc IBL, caustic paths) have heavy-tailed pixel sums and the
+    # normal approximation of the image mean is loose (measured: z up to 3.2, oracle vs oracle with two seeds gives the
+    # same); the full-size runs at 64 spp hold the 3-sigma bar without slack (tests/test_gpu_fullsize.py)
     assert z <= 4.0
 
 

@@ -59,6 +59,8 @@ struct Builder {
   std::vector<LrBvhNode> nodes;
   int max_depth = 0;
   float pad = 0.0f;
+  int leaf_target = kLeafTarget;     // items per leaf (1 when the items are subtrees: rebuild_top_sah)
+  const std::vector<int>* weight = nullptr;   // triangles an item stands for in the SAH cost (null: 1 each)
 
   Box bounds(int begin, int end) const {
     Box b; b.reset();
@@ -95,7 +97,7 @@ struct Builder {
         for (int i = begin; i < end; i++) {
           int b = (int)((centroid[order[i]][axis] - cb.lo[axis]) * scale);
           b = std::min(std::max(b, 0), kBins - 1);
-          bin_box[b].grow(tri_box[order[i]]); bin_n[b]++;
+          bin_box[b].grow(tri_box[order[i]]); bin_n[b] += weight ? (*weight)[order[i]] : 1;
         }
         float right_area[kBins]; int right_n[kBins];
         Box acc; acc.reset(); int cnt = 0;
@@ -142,7 +144,7 @@ struct Builder {
     for (int slot = 0; slot < 2; slot++) {
       const int b = range[slot][0], e = range[slot][1], cnt = e - b;
       const Box cbx = bounds(b, e);
-      bool leaf = cnt <= kLeafTarget;
+      bool leaf = cnt <= leaf_target;
       if (!leaf && cnt <= kLeafMax && depth + 1 >= kStackGuardDepth) leaf = true;
       if (leaf) {
         LrBvhNode tmp = nodes[me]; store_child(tmp, slot, cbx, leaf_code(b, cnt), cnt); nodes[me] = tmp;
@@ -163,14 +165,14 @@ struct Builder {
   // shifted: byte for byte the array the sequential build_inner emits (tests/test_host_frontend.py compares them).
   std::vector<LrBvhNode> build_forked(int begin, int end, const Box& box, int depth, int forks, int& depth_max) const {
     if (forks <= 0 || end - begin < kParallelGrain) {
-      Builder local{tri_box, centroid, order, {}, 0, pad};
+      Builder local{tri_box, centroid, order, {}, 0, pad, leaf_target, weight};
       local.nodes.reserve((size_t)(end - begin) / 2 + 16);
       local.build_inner(begin, end, box, depth);
       depth_max = local.max_depth;
       return std::move(local.nodes);
     }
     depth_max = depth + 1;
-    Builder self{tri_box, centroid, order, {}, 0, pad};            // partition / bounds / store_child on the shared arrays
+    Builder self{tri_box, centroid, order, {}, 0, pad, leaf_target, weight};            // partition / bounds / store_child on the shared arrays
     const int mid = self.partition(begin, end, box, depth);
     const int range[2][2] = {{begin, mid}, {mid, end}};
     Box cbx[2];
@@ -180,7 +182,7 @@ struct Builder {
     for (int slot = 0; slot < 2; slot++) {
       const int cnt = range[slot][1] - range[slot][0];
       cbx[slot] = self.bounds(range[slot][0], range[slot][1]);
-      leaf[slot] = cnt <= kLeafTarget || (cnt <= kLeafMax && depth + 1 >= kStackGuardDepth);
+      leaf[slot] = cnt <= leaf_target || (cnt <= kLeafMax && depth + 1 >= kStackGuardDepth);
     }
     auto run = [&](int slot) { sub[slot] = build_forked(range[slot][0], range[slot][1], cbx[slot], depth + 1, forks - 1, sub_depth[slot]); };
     if (!leaf[0] && !leaf[1]) {
@@ -256,6 +258,92 @@ static void peel_outliers(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>&
     }
     depth -= 1;
   }
+}
+
+// The top of a device-built tree, rebuilt with SAH on the host (the hierarchical-LBVH idea).  A radix tree splits space at
+// Morton-cell boundaries whatever the geometry; most of what that costs a traversal is decided in the upper levels, where every
+// ray passes.  The subtrees of at most `cut` triangles stay as the device built them; the nodes above them — a few thousand —
+// are replaced by a binned-SAH tree over the subtrees' boxes, written into the same node slots (a binary tree over M items has
+// M - 1 inner nodes either way; the root stays node 0).  Node order is no longer depth-first, which nothing depends on after
+// peel_outliers has run.  Returns the new depth of the tree.
+static int rebuild_top_sah(std::vector<LrBvhNode>& nodes, int cut, int max_depth) {
+  const int n_nodes = (int)nodes.size();
+  // triangles below every node: children follow their parent in the builders' depth-first layout
+  std::vector<int> cnt(n_nodes, 0), below(n_nodes, 1);       // below: depth of the subtree rooted at the node, in nodes
+  for (int i = n_nodes - 1; i >= 0; i--)
+    for (int k = 0; k < 2; k++) {
+      const int c = nodes[i].c[k];
+      cnt[i] += c >= 0 ? cnt[c] : nodes[i].n[k];
+      if (c >= 0) below[i] = std::max(below[i], below[c] + 1);
+    }
+  const int old_depth = n_nodes > 0 ? below[0] : 0;
+  if (n_nodes < 8 || cnt[0] <= cut) return old_depth;
+  struct Item { float box[6]; int code; int count; int depth; };
+  std::vector<Item> items;
+  std::vector<int> slots;                                    // the nodes above the cut, root first
+  {
+    std::vector<int> todo{0};
+    while (!todo.empty()) {
+      const int i = todo.back();
+      todo.pop_back();
+      slots.push_back(i);
+      for (int k = 1; k >= 0; k--) {
+        const int c = nodes[i].c[k];
+        if (c >= 0 && cnt[c] > cut) { todo.push_back(c); continue; }
+        Item it;
+        std::memcpy(it.box, nodes[i].f + 6 * k, sizeof(it.box));
+        it.code = c; it.count = nodes[i].n[k]; it.depth = c >= 0 ? below[c] : 0;
+        items.push_back(it);
+      }
+    }
+  }
+  const int m = (int)items.size();
+  if (m < 4 || (int)slots.size() != m - 1) return old_depth;
+  std::vector<Box> box(m);
+  std::vector<Vec3> centroid(m);
+  std::vector<int> order(m);
+  Box all; all.reset();
+  for (int i = 0; i < m; i++) {
+    for (int a = 0; a < 3; a++) { box[i].lo[a] = items[i].box[a]; box[i].hi[a] = items[i].box[3 + a]; }
+    centroid[i] = vec3(0.5f * (box[i].lo[0] + box[i].hi[0]), 0.5f * (box[i].lo[1] + box[i].hi[1]), 0.5f * (box[i].lo[2] + box[i].hi[2]));
+    order[i] = i;
+    all.grow(box[i]);
+  }
+  std::vector<int> weight(m);
+  for (int i = 0; i < m; i++) weight[i] = items[i].code >= 0 ? cnt[items[i].code] : items[i].count;
+  Builder top{box, centroid, order, {}, 0, 0.0f, 1, &weight};   // pad 0: the items' boxes are padded already; one item per leaf; SAH weighs an item by its triangles
+  top.nodes.reserve(m);
+  top.build_inner(0, m, all, 0);
+  if ((int)top.nodes.size() != m - 1) return old_depth;
+  // depth of the stitched tree, and a check that every leaf of the top tree is ONE item; nothing is written before both hold
+  int new_depth = 0;
+  {
+    std::vector<std::pair<int, int>> todo{{0, 1}};
+    while (!todo.empty()) {
+      const std::pair<int, int> cur = todo.back();
+      todo.pop_back();
+      for (int k = 0; k < 2; k++) {
+        const int c = top.nodes[cur.first].c[k];
+        if (c >= 0) { todo.push_back({c, cur.second + 1}); continue; }
+        if (((~c) & 7) != 0) return old_depth;               // a leaf of several items (only beyond depth 60): keep the old top
+        new_depth = std::max(new_depth, cur.second + items[order[(~c) >> 3]].depth);
+      }
+    }
+  }
+  if (new_depth >= max_depth) return old_depth;
+  for (int j = 0; j < m - 1; j++) {
+    LrBvhNode nd = top.nodes[j];
+    for (int k = 0; k < 2; k++) {
+      if (nd.c[k] >= 0) { nd.c[k] = slots[nd.c[k]]; nd.n[k] = 0; }
+      else {
+        const Item& it = items[order[(~nd.c[k]) >> 3]];        // the subtree (or device leaf) the one-item leaf stands for
+        nd.c[k] = it.code; nd.n[k] = it.count;
+        std::memcpy(nd.f + 6 * k, it.box, sizeof(it.box));
+      }
+    }
+    nodes[slots[j]] = nd;
+  }
+  return new_depth;
 }
 
 int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, int& depth_out, float& seconds_out, int& n_flat_out,
@@ -358,6 +446,9 @@ int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, 
     if (int rc = build_bvh_device(tris, n, 4e-6f * extent + 1e-30f, kLeafTarget, Builder::kStackGuardDepth, nodes_out, depth_out, sec, kernel_ms)) return rc;
     if (depth_out < Builder::kStackGuardDepth) {
       peel_outliers(tris, nodes_out, depth_out, n_flat_out);
+      int cut = 512;                                           // LR_BVH_TOP_CUT: development knob (0 = keep the radix tree's top)
+      if (const char* e = std::getenv("LR_BVH_TOP_CUT")) cut = std::atoi(e);
+      if (cut > 0) depth_out = rebuild_top_sah(nodes_out, cut, Builder::kStackGuardDepth);
       if (builder_used) *builder_used = LR_BVH_DEVICE;
       if (device_kernel_ms) *device_kernel_ms = kernel_ms;
       seconds_out = std::chrono::duration<float>(std::chrono::steady_clock::now() - t0).count();
@@ -414,6 +505,8 @@ int build_bvh(std::vector<LrTriangle>& tris, std::vector<LrBvhNode>& nodes_out, 
   nodes_out.swap(bld.nodes);
   depth_out = bld.max_depth;
   peel_outliers(tris, nodes_out, depth_out, n_flat_out);
+  // test hook (tests/test_host_frontend.py): the stitching code of the device path, run over a host-built tree
+  if (const char* e = std::getenv("LR_BVH_TOP_CUT_HOST")) if (std::atoi(e) > 0) depth_out = rebuild_top_sah(nodes_out, std::atoi(e), Builder::kStackGuardDepth);
   seconds_out = std::chrono::duration<float>(std::chrono::steady_clock::now() - t0).count();
   return LR_OK;
 }

@@ -649,3 +649,32 @@ def test_scene_trees_contain_their_triangles(lr, assets, name):
     if name == "welcome-2018":
         # the light quad hangs 2000 units above the mesh: peeled into the flat list (14 large triangles + 2)
         assert desc.n_flat_triangles == 16
+
+
+@pytest.mark.parametrize("cut", [4, 64, 512, 100000])
+def test_top_rebuild_of_a_tree_keeps_it_a_tree_over_the_same_triangles(lr, assets, monkeypatch, cut):
+    """rebuild_top_sah (bvh_build.cpp) replaces the nodes above the subtrees of <= `cut` triangles by a binned-SAH tree over
+    those subtrees' boxes, in place.  It is the post-pass of the DEVICE builder; LR_BVH_TOP_CUT_HOST runs the same code over
+    the host-built tree so that the stitching is checked without a GPU: the result must be a tree over exactly the same
+    triangles, every triangle inside its leaf's and every ancestor's box, the declared depth an upper bound — and the
+    oracle-independent nearest hits cannot change (topology independence), which the GPU suite checks for the device path."""
+    plain = load_scene(lr, "sample", (64, 64))
+    n_plain, depth_plain = plain.desc.contents.n_nodes, plain.desc.contents.bvh_depth
+    monkeypatch.setenv("LR_BVH_TOP_CUT_HOST", str(cut))
+    d = load_scene(lr, "sample", (64, 64))
+    desc = d.desc.contents
+    assert desc.n_nodes == n_plain and desc.n_flat_triangles == plain.desc.contents.n_flat_triangles
+    depth = _check_tree(desc)
+    assert depth <= desc.bvh_depth < 60
+    if cut >= 100000:
+        assert desc.bvh_depth == depth_plain                       # nothing above the cut: untouched
+    # the triangles are where the first build put them (the rebuild moves no triangle)
+    a = np.ctypeslib.as_array(C.cast(plain.desc.contents.triangles, C.POINTER(C.c_float)), shape=(desc.n_triangles, 11))
+    b = np.ctypeslib.as_array(C.cast(desc.triangles, C.POINTER(C.c_float)), shape=(desc.n_triangles, 11))
+    assert np.array_equal(a, b)
+    # lr_scene_create's validation (a tree, every node reached once, depth below the device stack) — fails only for want of a device
+    h = C.c_void_p()
+    rc = lr.load_library().lr_scene_create(d.desc, C.byref(h))
+    assert rc in (0, -2), lr.load_library().lr_last_error()
+    if rc == 0:
+        lr.load_library().lr_scene_destroy(h)

@@ -397,8 +397,8 @@ int build_bvh_device(std::vector<LrTriangle>& tris, int n_tree, float pad, int l
       }
       radix_tree_kernel<<<(n - 1 + kThreads - 1) / kThreads, kThreads>>>(d_code[cur], d_index[cur], n, d_child, d_parent);
       fit_kernel<<<blocks, kThreads>>>(d_index[cur], d_tri_box, n, d_child, d_parent, d_node_box, d_info, d_arrived, leaf_target);
-      emit_kernel<<<(n - 1 + kThreads - 1) / kThreads, kThreads>>>(n, d_child, d_parent, d_info, d_node_box, d_index[cur], d_in, d_out, d_nodes, pad, d_depth);
-      e = cudaGetLastError();
+      if (e == cudaSuccess) emit_kernel<<<(n - 1 + kThreads - 1) / kThreads, kThreads>>>(n, d_child, d_parent, d_info, d_node_box, d_index[cur], d_in, d_out, d_nodes, pad, d_depth);
+      if (e == cudaSuccess) e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaEventRecord(ev1, 0);
     NodeInfo root{};

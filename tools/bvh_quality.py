@@ -16,14 +16,15 @@ for name, res, spp, tris in (("sample", (1920, 1370), 16, 144046), ("welcome-201
         if kind == "host":
             d.rebuild_bvh("host"); sec = d.rebuild_bvh("host")
         else:
-            os.environ["LR_BVH_TOP_CUT"] = kind
+            cut = kind.rpartition(":")[2]                       # "512" or "lbvh:512"
+            os.environ["LR_BVH_TOP_CUT"] = cut
             d.rebuild_bvh("device"); sec = d.rebuild_bvh("device")
         s = d.scene()
         best = None
         for rep in range(3):
             img, _, st = s.render(spp=spp, seed=rep)
             best = st if best is None or st["kernel_ms"] < best["kernel_ms"] else best
-        print("%-13s %8d tris  tree %-12s build %8.1f ms  nodes %7d depth %2d  render %7.2f ms  %6.0f Msamples/s" % (
-            name, d.config.n_prims, "host SAH" if kind == "host" else "device cut " + kind, 1e3 * sec, d.desc.contents.n_nodes, d.desc.contents.bvh_depth,
+        print("%-13s %8d tris  tree %-16s build %8.1f ms (kernels %6.2f)  nodes %7d depth %2d  render %7.2f ms  %6.0f Msamples/s" % (
+            name, d.config.n_prims, "host SAH" if kind == "host" else "device " + kind, 1e3 * sec, d.config.bvh_device_kernel_ms if kind != "host" else 0.0, d.desc.contents.n_nodes, d.desc.contents.bvh_depth,
             best["kernel_ms"], best["samples"] / best["kernel_ms"] / 1e3), flush=True)
         s.close()

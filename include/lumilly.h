@@ -172,7 +172,9 @@ typedef struct LrStats {
   int32_t splits;              /* splits actually used                            */
 } LrStats;
 
-typedef struct LrScene LrScene;   /* opaque, owns device memory on the current device */
+typedef struct LrScene LrScene;   /* opaque; owns device memory on the device that was current at lr_scene_create (lr_init).
+                                     Every entry point that takes a scene (or a film of it) switches the calling thread to
+                                     that device for the call and restores the caller's device on return.               */
 
 /* ---- lifetime ---- */
 int lr_abi_version(void);

@@ -53,6 +53,19 @@ static cudaError_t dev_alloc(void** p, size_t bytes) {
 }
 static void dev_free(void* p) { if (p) cudaFreeAsync(p, 0); }
 
+// Every entry point that works on a scene runs on the device that owns it, whichever device the calling thread has current
+// (a host that talks to several GPUs switches devices between calls); the caller's device is restored on return.
+struct OnDevice {
+  int prev = -1;
+  explicit OnDevice(int device) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != device && cudaSetDevice(device) == cudaSuccess) prev = cur;
+  }
+  ~OnDevice() { if (prev >= 0) cudaSetDevice(prev); }
+  OnDevice(const OnDevice&) = delete;
+  OnDevice& operator=(const OnDevice&) = delete;
+};
+
 static inline float4 mk4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 static inline float as_float(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
 
@@ -384,6 +397,8 @@ static int ensure_scratch(float** buf, size_t* have, size_t need) {
 }
 
 int lr_render_accumulate_device(const LrScene* s, const LrRenderParams* p, float* d_sum, float* d_sumsq, void* cuda_stream) {
+  if (!s) return fail(LR_ERR_INVALID, "null argument");
+  const OnDevice on(s->device);
   DevParams dp;
   if (int rc = resolve_params(s, p, dp)) return rc;
   if (!d_sum) return fail(LR_ERR_INVALID, "d_sum is null");
@@ -429,6 +444,8 @@ int lr_render_accumulate_device(const LrScene* s, const LrRenderParams* p, float
 
 int lr_stats_fetch(const LrScene* s, void* cuda_stream, LrStats* stats) {
   if (!s || !stats) return fail(LR_ERR_INVALID, "null argument");
+  const OnDevice on(s->device);
+  if (!s || !stats) return fail(LR_ERR_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)cuda_stream;
   LR_CUDA(cudaStreamSynchronize(st));
   if (s->ev_pending) {
@@ -451,6 +468,8 @@ int lr_stats_fetch(const LrScene* s, void* cuda_stream, LrStats* stats) {
 }
 
 int lr_render(const LrScene* s, const LrRenderParams* p, float* out_rgb, float* out_sumsq, LrStats* stats) {
+  if (!s) return fail(LR_ERR_INVALID, "null argument");
+  const OnDevice on(s->device);
   DevParams dp;
   if (int rc = resolve_params(s, p, dp)) return rc;
   if (!out_rgb) return fail(LR_ERR_INVALID, "out_rgb is null");
@@ -481,6 +500,8 @@ int lr_render(const LrScene* s, const LrRenderParams* p, float* out_rgb, float* 
 }
 
 int lr_render_aov(const LrScene* s, const LrRenderParams* p, int32_t kind, float* out) {
+  if (!s) return fail(LR_ERR_INVALID, "null argument");
+  const OnDevice on(s->device);
   if (!s || !p || !out) return fail(LR_ERR_INVALID, "null argument");
   if (kind != LR_AOV_NORMAL && kind != LR_AOV_DEPTH) return fail(LR_ERR_INVALID, "unknown AOV kind");
   LrRenderParams q = *p;
@@ -778,6 +799,8 @@ int lr_render_multi(const LrSceneDesc* desc, const LrRenderParams* p, int32_t n_
 }
 
 int lr_trace_primary(const LrScene* s, float u, float v, float ua, float va, int32_t* prim, float* t) {
+  if (!s) return fail(LR_ERR_INVALID, "null argument");
+  const OnDevice on(s->device);
   if (!s || !prim || !t) return fail(LR_ERR_INVALID, "null argument");
   if (int rc = ensure_device()) return rc;
   const size_t n = (size_t)s->width * s->height;
@@ -799,6 +822,8 @@ int lr_trace_rays(const LrScene* s, int64_t n, const float* origins, const float
 
 int lr_trace_rays_query(const LrScene* s, int64_t n, const float* origins, const float* directions, int32_t query, int32_t* prim, float* t,
                         float* normal) {
+  if (!s) return fail(LR_ERR_INVALID, "bad argument");
+  const OnDevice on(s->device);
   if (!s || !origins || !directions || !prim || !t || n < 0) return fail(LR_ERR_INVALID, "bad argument");
   if (query != LR_QUERY_STRICT && query != LR_QUERY_RENDER) return fail(LR_ERR_INVALID, "unknown query kind");
   if (n == 0) return LR_OK;
@@ -842,6 +867,8 @@ struct FilmHeader {                      // checkpoint file: this header, then c
 };
 
 int film_alloc(const LrScene* s, const LrRenderParams* p, int want_sumsq, LrFilm** out) {
+  if (!s) return fail(LR_ERR_INVALID, "null argument");
+  const OnDevice on(s->device);
   if (!s || !p || !out) return fail(LR_ERR_INVALID, "null argument");
   *out = nullptr;
   LrRenderParams probe = *p;
@@ -872,6 +899,8 @@ extern "C" {
 int lr_film_create(const LrScene* s, const LrRenderParams* p, int32_t want_sumsq, LrFilm** out) { LR_GUARDED(film_alloc(s, p, want_sumsq, out)); }
 
 void lr_film_destroy(LrFilm* f) {
+  if (!f) return;
+  const OnDevice on(f->scene->device);
   if (!f) return;
   cudaDeviceSynchronize();
   dev_free(f->d_sum);
@@ -904,6 +933,8 @@ int lr_film_render(LrFilm* f, int32_t spp_count, LrStats* stats) {
 }
 
 int lr_film_read(const LrFilm* f, float* out_rgb, float* out_sumsq) {
+  if (!f) return fail(LR_ERR_INVALID, "null argument");
+  const OnDevice on(f->scene->device);
   if (!f || !out_rgb) return fail(LR_ERR_INVALID, "null argument");
   if (out_sumsq && !f->d_sumsq) return fail(LR_ERR_INVALID, "the film was created without sums of squares");
   if (f->spp_done <= 0) return fail(LR_ERR_INVALID, "the film holds no samples yet");
@@ -920,6 +951,8 @@ int lr_film_read(const LrFilm* f, float* out_rgb, float* out_sumsq) {
 }
 
 static int film_save_body(const LrFilm* f, const char* path) {
+  if (!f) return fail(LR_ERR_INVALID, "null argument");
+  const OnDevice on(f->scene->device);
   if (!f || !path) return fail(LR_ERR_INVALID, "null argument");
   const size_t n = (size_t)f->crop_w * f->crop_h * 3;
   std::vector<float> host(n * (f->d_sumsq ? 2 : 1));

@@ -291,6 +291,21 @@ def test_render_multi_single_process(scenes, lr, gpu, monkeypatch):
     few, _, stf = d.render_multi([1, 0], spp=1, seed=13, splits=1)
     solo, _, sts = s.render(spp=1, seed=13, splits=1)
     assert np.array_equal(few, solo) and stf["rays"] == sts["rays"]
+    # a scene stays on the device it was created on, whichever device the calling thread makes current afterwards
+    lr.init(1)
+    s1 = d.scene()                                              # lives on device 1
+    on1, _, st_on1 = s1.render(spp=6, seed=13, splits=1)
+    lr.init(0)
+    again1, _, _ = s1.render(spp=6, seed=13, splits=1)          # called with device 0 current: runs on device 1
+    depth1 = s1.render_aov("depth", spp=1, seed=13)
+    film1 = s1.film(seed=13, splits=1)
+    film1.render(6)
+    assert np.array_equal(on1, ref) and np.array_equal(again1, ref) and st_on1["rays"] == st["rays"]
+    assert np.array_equal(film1.read(), ref) and np.array_equal(depth1, s.render_aov("depth", spp=1, seed=13))
+    film1.close()
+    s1.close()
+    still, _, _ = s.render(spp=6, seed=13, splits=1)            # the device-0 scene is untouched by all that
+    assert np.array_equal(still, ref)
     # the handle form (scenes, streams, peer mappings set up once): same bits as the one-shot call, call after call
     ms = d.multi_scene([0, 1])
     for _ in range(3):

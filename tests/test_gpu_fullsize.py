@@ -282,3 +282,37 @@ def test_device_built_bvh_gives_the_same_hits_and_the_same_image(full, lr, case)
     assert (pd == po).mean() >= 0.9999
     d2.rebuild_bvh("host")                            # leave the shared fixture as the other tests expect it
     assert d2.config.bvh_builder == 0 and d2.desc.contents.n_nodes == host_nodes
+
+
+@pytest.mark.parametrize("name,res,spp", [("primitive", (2048, 2048), 16), ("new-cbox", (256, 256), 64), ("brdf", (960, 540), 64)])
+def test_flat_only_configs_at_their_full_size(lr, orc, gpu, assets, name, res, spp):
+    """BASELINE configs 1-3 (no mesh: spheres and a handful of triangles, all in the flat list) at the film size and spp the
+    config names: primary hits over the whole film (index equal on >= 99.99 %, t bit-equal for the ideal pinhole), replay of
+    the whole film at 2 spp with equal ray counts, and the statistical comparison at the config's spp without slack terms."""
+    d = lr.Description(os.path.join(SCENES, name + ".toml"), asset_root=ROOT, resolution=res)
+    assert (d.config.width, d.config.height) == res and d.desc.contents.n_nodes == 0
+    s = d.scene()
+    o = orc.OracleScene(d.desc, keepalive=d)
+    for jitter in ((0.5, 0.5, 0.5, 0.5), (0.137, 0.859, 0.301, 0.644)):
+        pg, tg = s.trace_primary(*jitter)
+        po, to = o.trace_primary(*jitter, traversal=0)
+        both = (pg == po) & (po >= 0)
+        assert (pg == po).mean() >= 0.9999 and np.array_equal(tg[both], to[both])
+    img, sq, st = s.render(spp=2, seed=11, splits=1, sumsq=True)
+    ref_sum, ref_sq, ost = o.render(make_params(lr, d.config, spp=2, seed=11), traversal=0, rng_mode=0, math_mode=1)
+    frac = np.isclose(img, ref_sum / 2, rtol=1e-4, atol=1e-5).all(-1).mean()
+    assert st["rays"] == ost["rays"] and frac >= 0.999 and st["nonfinite_samples"] == ost["nonfinite_samples"]
+    img, sq, st = s.render(spp=spp, seed=5, sumsq=True)
+    ref_sum, ref_sq, ost = o.render(make_params(lr, d.config, spp=spp, seed=99), traversal=0, rng_mode=1, math_mode=0)
+    ok = np.isfinite(img).all(-1) & np.isfinite(ref_sum).all(-1)
+    a, b = img[ok].astype(np.float64), (ref_sum[ok] / spp).astype(np.float64)
+    va = np.maximum(sq[ok] / spp - a ** 2, 0.0) * spp / (spp - 1)
+    vb = np.maximum(ref_sq[ok] / spp - b ** 2, 0.0) * spp / (spp - 1)
+    se = np.sqrt(va / spp + vb / spp)
+    inf = se > 0
+    within = (np.abs(a - b)[inf] <= 3.0 * se[inf]).mean()
+    exact = np.isclose(a[~inf], b[~inf], rtol=1e-5, atol=1e-7).mean() if (~inf).any() else 1.0
+    z = abs(a.mean() - b.mean()) / (np.sqrt((se ** 2).sum()) / a.size)
+    print("%s %dx%d at %d spp: replay agreement %.5f (rays %d = %d); within-3sigma %.4f, zero-variance channels equal %.4f, image-mean z %.2f, "
+          "non-finite gpu %d oracle %d" % (name, res[0], res[1], spp, frac, st["rays"], ost["rays"], within, exact, z, st["nonfinite_samples"], ost["nonfinite_samples"]))
+    assert ok.mean() >= 0.999 and within >= 0.99 and exact >= 0.99 and z <= 3.5

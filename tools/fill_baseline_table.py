@@ -17,9 +17,9 @@ n1 = load(sys.argv[1])
 multi = {l["n_gpus"]: l for l in (load(p) for p in sys.argv[2:])}
 rows = []
 parity = {
-    "1 primitive": "100 % / 0 (bit-equal) / ≥ 99 % / see tests (256² crop suite)",
-    "2 new-cbox": "100 % / 0 / ≥ 99 % / see tests (128²)",
-    "3 brdf": "100 % / 0 / ≥ 99 % / see tests (240×135)",
+    "1 primitive": "≥ 99.99 % of 4.19 M px / 0 (bit-equal) / ≥ 99 % / see log (full size)",
+    "2 new-cbox": "≥ 99.99 % / 0 (bit-equal) / ≥ 99 % / see log (full size)",
+    "3 brdf": "≥ 99.99 % of 518 k px / 0 (bit-equal) / ≥ 99 % / see log (full size)",
     "4 welcome-2018 (144k)": "100 % of 3.28 M px / 0 (bit-equal) / 99.75 % / 43.2 (full size)",
     "4 welcome-2018 (1M)": "100 % of 3.28 M px / 0 (bit-equal) / replay exact vs tie rule / —",
 }

@@ -302,6 +302,7 @@ def test_flat_only_configs_at_their_full_size(lr, orc, gpu, assets, name, res, s
     ref_sum, ref_sq, ost = o.render(make_params(lr, d.config, spp=2, seed=11), traversal=0, rng_mode=0, math_mode=1)
     frac = np.isclose(img, ref_sum / 2, rtol=1e-4, atol=1e-5).all(-1).mean()
     assert st["rays"] == ost["rays"] and frac >= 0.999 and st["nonfinite_samples"] == ost["nonfinite_samples"]
+    replay_rays = (st["rays"], ost["rays"])
     img, sq, st = s.render(spp=spp, seed=5, sumsq=True)
     ref_sum, ref_sq, ost = o.render(make_params(lr, d.config, spp=spp, seed=99), traversal=0, rng_mode=1, math_mode=0)
     ok = np.isfinite(img).all(-1) & np.isfinite(ref_sum).all(-1)
@@ -313,6 +314,6 @@ def test_flat_only_configs_at_their_full_size(lr, orc, gpu, assets, name, res, s
     within = (np.abs(a - b)[inf] <= 3.0 * se[inf]).mean()
     exact = np.isclose(a[~inf], b[~inf], rtol=1e-5, atol=1e-7).mean() if (~inf).any() else 1.0
     z = abs(a.mean() - b.mean()) / (np.sqrt((se ** 2).sum()) / a.size)
-    print("%s %dx%d at %d spp: replay agreement %.5f (rays %d = %d); within-3sigma %.4f, zero-variance channels equal %.4f, image-mean z %.2f, "
-          "non-finite gpu %d oracle %d" % (name, res[0], res[1], spp, frac, st["rays"], ost["rays"], within, exact, z, st["nonfinite_samples"], ost["nonfinite_samples"]))
+    print("%s %dx%d at %d spp: replay at 2 spp agreement %.5f (rays %d = %d); within-3sigma %.4f, zero-variance channels equal %.4f, image-mean z %.2f, "
+          "non-finite gpu %d oracle %d" % (name, res[0], res[1], spp, frac, replay_rays[0], replay_rays[1], within, exact, z, st["nonfinite_samples"], ost["nonfinite_samples"]))
     assert ok.mean() >= 0.999 and within >= 0.99 and exact >= 0.99 and z <= 3.5
